@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Benchmark of the HyperReel per-ray rendering hot path on B200 (contract: see the task prompt / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mlp fp32|bf16x3]
+
+One "step" = one pass of the hot path (sample net -> intersect -> VM gather -> decode -> composite) over one
+synthetic batch of 65 536 rays x 32 samples per GPU, Technicolor-shape model (technicolor_z_plane: C_in=8,
+K=12 keyframes of 50 frames, comps [8,0,0], SH-27, final-size 1007x1007x503 grid, 62 MiB of tables),
+seeded random-init sample net, "trained-like" density tables.  Weak scaling: every rank renders its own
+65 536-ray shard, then the finished [N/G,3] tiles are gathered with one NCCL all_gather (inside the timed
+region).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 65536
+WORKLOAD = "technicolor_z_plane"
+N_VOXELS = 512000000  # final grid 1007x1007x503 (utils/tensorf_utils.py:65-68)
+DENSITY_GAIN = 30.0
+PARAM_SEED = 11
+CPU_SAMPLE_RAYS = 8192
+L2_FLUSH_BYTES = 512 << 20
+
+
+def algorithmic_bytes_per_ray(sig) -> int:
+    """4*C_in + 12 + S * sum_fields sum_planes 4*C*(4 + T), T = 4 dynamic / 2 static."""
+    c = sig.cfg
+    T = 4 if c.dynamic else 2
+    per_sample = 0
+    for comps in (c.n_sigma, c.n_app):
+        for i in range(3):
+            per_sample += 4 * int(comps[i]) * (4 + T)
+    return 4 * c.c_in + 12 + c.n_samples * per_sample
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max((int(r[1]) for r in self.rows if r[1].isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+
+
+def build_workload():
+    import hyperreel_b200 as hb
+    from hyperreel_b200.state import seeded_state_dict
+
+    cfg, ds = hb.configs.get(WORKLOAD, n_voxels=N_VOXELS)
+    sig = hb.lower(cfg, ds)
+    sd = seeded_state_dict(sig, seed=PARAM_SEED, density_gain=DENSITY_GAIN)
+    return hb, cfg, ds, sig, sd
+
+
+def time_cpu_port(cfg, ds, sd, sig, hb, steps: int, warmup: int, rays_n: int):
+    """The reference's CPU path restated (oracle port, same torch ops as the reference: gather='grid_sample'),
+    all host threads, on a bounded sample of the same workload."""
+    import torch
+    from oracle.hyperreel_oracle import HyperReelOracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    orc = HyperReelOracle(hb.config.to_plain(cfg), ds, sd, gather="grid_sample")
+    rays = hb.rays.for_signature(sig, rays_n, seed=5)
+    for _ in range(warmup):
+        orc.render(rays.clone())
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        orc.render(rays.clone())
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return rays_n / med / 1e6, sum(ts) / len(ts) * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    hb, cfg, ds, sig, sd = build_workload()
+    mrays, ms, cores = time_cpu_port(cfg, ds, sd, sig, hb, max(args.steps, 1), max(min(args.warmup, 1), 1), CPU_SAMPLE_RAYS)
+    sample = f"{CPU_SAMPLE_RAYS} rays x {sig.n_samples} samples per step (bounded sample of the 65536-ray batch), torch CPU ops, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "Mrays/s at 65k-ray x 32-sample batch", "value": mrays, "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD} 65536 rays x 32 samples, grid 1007x1007x503, K=12", "parallelism": "host cpu"},
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (hyperreel_b200 has no CPU path); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    hb, cfg, ds, sig, sd = build_workload()
+    model = hb.LightfieldModel(cfg, dataset=ds, mlp_mode=args.mlp)
+    render = hb.RenderLightfield(model, None, cfg.render, net_chunk=1 << 22)
+    render.load_state_dict(sd, strict=False)
+    render.eval()
+    n = args.rays
+    # every rank gets its own shard of the global ray batch (contiguous ranges)
+    rays_host = hb.rays.for_signature(sig, n, seed=5 + rank).pin_memory()
+    rays = rays_host.to(dev)
+    tiles = torch.empty((world, n, 3), device=dev) if world > 1 else None
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+
+    def step():
+        rgb = render(rays)["rgb"]
+        if world > 1:
+            dist.all_gather_into_tensor(tiles.view(world * n, 3), rgb)  # the single collective: finished pixel tiles
+        return rgb
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    model.timing(True)
+    launches0 = model.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()  # evict L2 between timed iterations (tables 62 MiB < 126 MB L2)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tm = model.timing_read()
+    model.timing(False)
+    launches = model.launch_count() - launches0
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer API: pinned rays in, rgb out, copies inside the timed region ----
+    rgb_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        model.render_host(rays_host, rgb_host)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_t = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.render_host(rays_host, rgb_host)
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_ms = sum(e2e_t) / len(e2e_t) * 1e3
+    t2 = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_val = world * n / (float(t2.item()) * 1e-3) / 1e6
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        bpr = algorithmic_bytes_per_ray(sig)
+        achieved = (bpr * n / (tm["render_ms"] * 1e-3) / 1e9) if tm["render_ms"] > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "render_kernel_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            mr, _, cores = time_cpu_port(cfg, ds, sd, sig, hb, 3, 1, CPU_SAMPLE_RAYS)
+            cpu = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                   "sample": f"{CPU_SAMPLE_RAYS} rays x {sig.n_samples} samples (bounded sample), torch CPU ops, 1 warm-up + 3 runs, median"}
+        line = {
+            "metric": "Mrays/s at 65k-ray x 32-sample batch", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mlp == "fp32" else "f32 (sample net bf16x3 split on tcgen05, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD}: {n} rays x {sig.n_samples} samples per GPU, grid 1007x1007x503, K=12, comps [8,0,0], SH-27",
+                       "rays_per_gpu": n, "samples_per_ray": sig.n_samples, "parallelism": f"ray-shard x{world} + all_gather of rgb tiles",
+                       "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB memset)", "sample_net": args.mlp,
+                       "params": f"seed {PARAM_SEED}, density gain {DENSITY_GAIN} (trained-like)"},
+            "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n * sig.c_in * 4, "d2h_bytes_per_step": n * 12,
+                    "ms_per_step": float(t2.item())},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": traffic, "kernel": "render_kernel (fused intersect+gather+decode+composite)",
+                         "algorithmic_bytes_per_ray": bpr, "kernel_ms": tm["render_ms"], "peak_source": peak_src,
+                         "sample_net_kernel_ms": tm["mlp_ms"]},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mlp", default=os.environ.get("HR_BENCH_MLP", "fp32"), choices=["fp32", "bf16x3"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,485 @@
+// C-ABI of libhyperreel_b200.so (declared in include/hyperreel_b200.h).
+// Host-side glue only: parameter packing, workspace carving, kernel launches, timing.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "hr_common.cuh"
+#include "hr_mlp.cuh"
+#include "hyperreel_b200.h"
+
+namespace hr {
+cudaError_t launch_render(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
+                          const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
+                          cudaStream_t stream);
+}  // namespace hr
+
+static thread_local std::string g_err;
+
+int hr_fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#include "hr_handle.h"
+
+namespace {
+
+__global__ void pack_channel_last(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W) {
+  // src [C][H][W] (reference [1,C,H,W]) -> dst [H][W][C]
+  long long total = (long long)C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long hw = i / C;
+    dst[i] = src[(long long)c * H * W + hw];
+  }
+}
+
+// Wt[k][n] (k-major, zero padded) from the reference weight W[out][in] (nn.Linear layout).
+//   k -> source column: k < in_pad: (k < in_ch ? k : none) when the layer consumes the encoded input;
+//                        hidden rows follow.  n -> source row: last layer channel-major permutation.
+__global__ void pack_simt_layer(const float* __restrict__ Wsrc, const float* __restrict__ bsrc, float* __restrict__ Wt,
+                                float* __restrict__ bias, int Kp, int Np, int out_ch, int in_ch_src, int in_enc,
+                                int in_pad, int has_input, int has_hidden, int width, int perm_S, int perm_stride) {
+  long long total = (long long)Kp * Np;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total + Np; i += (long long)gridDim.x * blockDim.x) {
+    if (i >= total) {
+      int n = (int)(i - total);
+      int ns = n;
+      if (perm_S > 0 && n < out_ch) ns = (n % perm_S) * perm_stride + (n / perm_S);
+      bias[n] = (n < out_ch) ? bsrc[ns] : 0.0f;
+      continue;
+    }
+    int n = (int)(i % Np);
+    int k = (int)(i / Np);
+    float v = 0.0f;
+    if (n < out_ch) {
+      int ns = n;
+      if (perm_S > 0) ns = (n % perm_S) * perm_stride + (n / perm_S);  // n = c*S+s  <-  s*stride+c
+      int ks = -1;
+      if (has_input) {
+        if (k < in_pad) ks = (k < in_enc) ? k : -1;
+        else if (has_hidden) ks = in_enc + (k - in_pad);
+      } else {
+        ks = k;
+      }
+      if (ks >= 0 && ks < in_ch_src && (has_input || k < width)) v = Wsrc[(long long)ns * in_ch_src + ks];
+    }
+    Wt[i] = v;
+  }
+}
+
+__global__ void unpermute_heads(const float* __restrict__ src, float* __restrict__ dst, long long n, int S, int stride) {
+  // src [n][c*S+s] -> dst [n][s*stride+c]
+  long long total = n * (long long)S * stride;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long ray = i / (S * stride);
+    int rem = (int)(i % (S * stride));
+    int s = rem / stride, c = rem % stride;
+    dst[i] = src[ray * (long long)S * stride + c * S + s];
+  }
+}
+
+int grid_for(long long total) {
+  long long g = (total + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int dev_alloc(hr_handle* h, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+  if (e != cudaSuccess) return fail("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  h->owned.push_back(*p);
+  return 0;
+}
+
+// Copy a reference-layout tensor to the device if it is on the host (returns device pointer).
+int stage_in(const float* src, size_t count, int on_device, cudaStream_t st, std::vector<void*>& temps, const float** out) {
+  if (on_device) {
+    *out = src;
+    return 0;
+  }
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, count * sizeof(float));
+  if (e != cudaSuccess) return fail("cudaMalloc(temp %zu) failed: %s", count * sizeof(float), cudaGetErrorString(e));
+  temps.push_back(d);
+  e = cudaMemcpyAsync(d, src, count * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return fail("H2D of parameters failed: %s", cudaGetErrorString(e));
+  *out = (const float*)d;
+  return 0;
+}
+
+int validate(const hr_config& c) {
+  if (c.abi_version != HR_ABI_VERSION) return fail("hr_config.abi_version %d != %d", c.abi_version, HR_ABI_VERSION);
+  if (c.c_in < 6 || c.c_in > 16) return fail("unsupported c_in %d", c.c_in);
+  if (c.n_groups < 1 || c.n_groups > HR_MAX_GROUPS) return fail("unsupported n_groups %d", c.n_groups);
+  if (c.mlp_layers < 2 || c.mlp_layers > HR_MAX_LAYERS) return fail("unsupported mlp_layers %d", c.mlp_layers);
+  if (c.mlp_width != 128 && c.mlp_width != 256) return fail("unsupported mlp_width %d (128 or 256)", c.mlp_width);
+  if (c.mlp_in < 1 || c.mlp_in > 64) return fail("unsupported mlp_in %d", c.mlp_in);
+  if (c.mlp_skip != -1 && (c.mlp_skip < 1 || c.mlp_skip > c.mlp_layers - 2)) return fail("bad mlp_skip %d", c.mlp_skip);
+  if (c.n_samples < 1 || c.n_samples > HR_MAX_SAMPLES) return fail("unsupported n_samples %d (max %d)", c.n_samples, HR_MAX_SAMPLES);
+  if (c.mlp_out != c.n_samples * c.head_stride) return fail("mlp_out %d != S*head_stride %d", c.mlp_out, c.n_samples * c.head_stride);
+  if (c.off_z < 0) return fail("z_vals head is required");
+  if (c.isect_type == HR_ISECT_Z_PLANE && c.n_z != 1) return fail("z_plane needs 1 z channel");
+  if (c.isect_type == HR_ISECT_SPHERE && c.n_z != 4) return fail("sphere needs 4 z channels");
+  if (c.isect_type != HR_ISECT_Z_PLANE && c.isect_type != HR_ISECT_SPHERE) return fail("unsupported intersect type %d", c.isect_type);
+  if (c.contract_type != HR_CONTRACT_NONE && c.contract_type != HR_CONTRACT_MIPNERF) return fail("unsupported contract type");
+  if (c.use_flow && (c.off_flow < 0 || c.num_keyframes < 1 || c.num_frames < 1)) return fail("flow needs spatial_flow head and K,F");
+  if (c.use_offset && c.off_offset < 0) return fail("point_offset needs point_offset head");
+  if (c.use_color_scale_shift && (c.off_cscale < 0 || c.off_cshift < 0)) return fail("colour scale/shift heads missing");
+  if (c.dynamic && (c.num_keyframes < 1 || c.num_frames < 1)) return fail("dynamic net needs K,F");
+  for (int i = 0; i < 3; ++i)
+    if (c.n_sigma[i] != c.n_app[i]) return fail("n_lamb_sigma != n_lamb_sh not supported");
+  const int* s = c.n_sigma;
+  bool ok = (s[0] == 8 && s[1] == 0 && s[2] == 0) || (s[0] == 8 && s[1] == 4 && s[2] == 4) || (s[0] == 8 && s[1] == 8 && s[2] == 8);
+  if (!ok) return fail("unsupported component layout [%d,%d,%d]", s[0], s[1], s[2]);
+  if (c.shading == HR_SHADE_SH && c.app_dim != 27) return fail("SH shading needs app_dim 27");
+  if (c.shading == HR_SHADE_RGB && c.app_dim != 3) return fail("RGB shading needs app_dim 3");
+  if (c.shading != HR_SHADE_SH && c.shading != HR_SHADE_RGB) return fail("unsupported shading");
+  if (c.mlp_mode != HR_MLP_FP32_SIMT && c.mlp_mode != HR_MLP_BF16X3_TC) return fail("unsupported mlp_mode");
+  if (c.mlp_mode == HR_MLP_BF16X3_TC && c.mlp_width != 256) return fail("tensor-core sample net needs width 256");
+  return 0;
+}
+
+void derive(const hr_config& c, hr::Derived& d) {
+  double K = c.num_keyframes > 0 ? c.num_keyframes : 1, F = c.num_frames > 0 ? c.num_frames : 1;
+  double fac = K * (F - 1.0) / F;
+  d.time_fac = (float)fac;
+  d.time_inv_fac = (fac != 0.0) ? (float)(1.0 / fac) : 0.0f;
+  d.time_scale = (float)((F - 1.0) / F);
+  d.time_offset = (float)(0.5 / K);
+  d.kf_max = (float)(K - 1.0);
+  double ied = (double)c.contract_start_distance / (double)c.contract_end_distance;
+  d.inv_end_dist = (float)ied;
+  d.dist_scale_fac = (float)(1.0 / (1.0 - ied));
+  double ier = (double)c.contract_start_radius / (double)c.contract_end_radius;
+  d.inv_end_rad = (float)ier;
+  d.rad_scale_fac = (float)(1.0 / (1.0 - ier));
+}
+
+}  // namespace
+
+extern "C" {
+
+int hr_abi_version(void) { return HR_ABI_VERSION; }
+
+const char* hr_last_error(void) { return g_err.c_str(); }
+
+int hr_create(const hr_config* cfg, int device, hr_handle** out) {
+  if (!cfg || !out) return fail("hr_create: null argument");
+  *out = nullptr;
+  if (validate(*cfg)) return 1;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail("hr_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail("hr_create: device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("hr_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  CK(cudaSetDevice(device));
+  hr_handle* h = new (std::nothrow) hr_handle();
+  if (!h) return fail("hr_create: out of memory");
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  derive(h->cfg, h->dv);
+  memset(&h->tabs, 0, sizeof(h->tabs));
+  memset(&h->simt, 0, sizeof(h->simt));
+  memset(&h->tc, 0, sizeof(h->tc));
+  *out = h;
+  return 0;
+}
+
+int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
+  if (!h || !p) return fail("hr_upload: null argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const hr_config& c = h->cfg;
+  // release any previous pack
+  for (void* q : h->owned) cudaFree(q);
+  h->owned.clear();
+  h->uploaded = false;
+  h->tc_ready = false;
+  std::vector<void*> temps;
+  int rc = 0;
+
+  // ---- sample net ----
+  const int L = c.mlp_layers, W = c.mlp_width;
+  const int in_pad = (c.mlp_in + 15) / 16 * 16;
+  h->simt.in_pad = in_pad;
+  h->simt.n_layers = L;
+  h->simt.skip = c.mlp_skip;
+  const float* w_dev[HR_MAX_LAYERS] = {nullptr};
+  const float* b_dev[HR_MAX_LAYERS] = {nullptr};
+  for (int l = 0; l < L && !rc; ++l) {
+    if (!p->mlp_weight[l] || !p->mlp_bias[l]) { rc = fail("hr_upload: mlp layer %d missing", l); break; }
+    const bool first = (l == 0), last = (l == L - 1), skip = (l == c.mlp_skip);
+    const int in_src = first ? c.mlp_in : (skip ? c.mlp_in + W : W);
+    const int out_ch = last ? c.mlp_out : W;
+    const int Kp = first ? in_pad : (skip ? in_pad + W : W);
+    const int Np = last ? (c.mlp_out + W - 1) / W * W : W;
+    rc = stage_in(p->mlp_weight[l], (size_t)out_ch * in_src, p->on_device, st, temps, &w_dev[l]);
+    if (rc) break;
+    rc = stage_in(p->mlp_bias[l], (size_t)out_ch, p->on_device, st, temps, &b_dev[l]);
+    if (rc) break;
+    float *Wt = nullptr, *bias = nullptr;
+    if ((rc = dev_alloc(h, (void**)&Wt, (size_t)Kp * Np * sizeof(float)))) break;
+    if ((rc = dev_alloc(h, (void**)&bias, (size_t)Np * sizeof(float)))) break;
+    pack_simt_layer<<<grid_for((long long)Kp * Np + Np), 256, 0, st>>>(
+        w_dev[l], b_dev[l], Wt, bias, Kp, Np, out_ch, in_src, c.mlp_in, in_pad, (first || skip) ? 1 : 0, skip ? 1 : 0, W,
+        last ? c.n_samples : 0, c.head_stride);
+    h->simt.Wt[l] = Wt;
+    h->simt.bias[l] = bias;
+    h->simt.Kp[l] = Kp;
+    h->simt.Np[l] = Np;
+  }
+  if (!rc && c.mlp_mode == HR_MLP_BF16X3_TC) {
+    rc = hr::pack_mlp_tc(h, p, w_dev, b_dev, st);
+    if (!rc) h->tc_ready = true;
+  }
+
+  // ---- VM tables, channel-last ----
+  auto pack_tab = [&](const float* src, int C, int H, int Wd, const float** out) -> int {
+    *out = nullptr;
+    if (C == 0) return 0;
+    if (!src) return fail("hr_upload: table with C=%d missing", C);
+    const float* d = nullptr;
+    if (stage_in(src, (size_t)C * H * Wd, p->on_device, st, temps, &d)) return 1;
+    float* dst = nullptr;
+    if (dev_alloc(h, (void**)&dst, (size_t)C * H * Wd * sizeof(float))) return 1;
+    pack_channel_last<<<grid_for((long long)C * H * Wd), 256, 0, st>>>(d, dst, C, H, Wd);
+    *out = dst;
+    return 0;
+  };
+  int n_app_total = 0;
+  for (int i = 0; i < 3 && !rc; ++i) {
+    const int C = c.n_sigma[i];
+    n_app_total += c.n_app[i];
+    const int H2 = c.dynamic ? c.num_keyframes : 1;
+    hr::PlaneTab& ts = h->tabs.sig[i];
+    hr::PlaneTab& ta = h->tabs.app[i];
+    ts.C = C; ta.C = c.n_app[i];
+    ts.H = ta.H = p->plane_h[i];
+    ts.W = ta.W = p->plane_w[i];
+    ts.H2 = ta.H2 = H2;
+    ts.L = ta.L = p->second_len[i];
+    if (C > 0 && (ts.H < 2 || ts.W < 2 || ts.L < 2)) { rc = fail("hr_upload: plane %d too small (%dx%d, L=%d)", i, ts.H, ts.W, ts.L); break; }
+    if ((rc = pack_tab(p->sigma_plane[i], C, ts.H, ts.W, &ts.space))) break;
+    if ((rc = pack_tab(p->app_plane[i], C, ts.H, ts.W, &ta.space))) break;
+    // second factor: dynamic [C][K][L] -> [K][L][C]; static [C][L][1] -> [1][L][C]
+    if ((rc = pack_tab(p->sigma_second[i], C, H2, ts.L, &ts.second))) break;
+    if ((rc = pack_tab(p->app_second[i], C, H2, ts.L, &ta.second))) break;
+  }
+  if (!rc) {
+    if (!p->basis_mat) rc = fail("hr_upload: basis_mat missing");
+    else {
+      const float* d = nullptr;
+      size_t cnt = (size_t)c.app_dim * n_app_total;
+      rc = stage_in(p->basis_mat, cnt, p->on_device, st, temps, &d);
+      if (!rc) {
+        float* dst = nullptr;
+        rc = dev_alloc(h, (void**)&dst, cnt * sizeof(float));
+        if (!rc) {
+          cudaError_t e = cudaMemcpyAsync(dst, d, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st);
+          if (e != cudaSuccess) rc = fail("basis copy failed: %s", cudaGetErrorString(e));
+          h->tabs.basis = dst;
+          h->tabs.n_app_total = n_app_total;
+        }
+      }
+    }
+  }
+  cudaError_t le = cudaGetLastError();
+  if (!rc && le != cudaSuccess) rc = fail("hr_upload: pack kernel launch failed: %s", cudaGetErrorString(le));
+  if (!temps.empty()) {
+    cudaStreamSynchronize(st);
+    for (void* t : temps) cudaFree(t);
+  }
+  if (rc) return rc;
+  h->uploaded = true;
+  return 0;
+}
+
+int64_t hr_workspace_bytes(const hr_handle* h, int64_t n_rays) {
+  if (!h || n_rays < 0) return -1;
+  int64_t b = n_rays * (int64_t)h->cfg.mlp_out * (int64_t)sizeof(float);
+  return (b + 255) / 256 * 256 + 256;
+}
+
+static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, float* mlp_out, const hr::StageOut* so,
+                       void* workspace, int64_t ws_bytes, cudaStream_t st) {
+  if (!h) return fail("hr_render: null handle");
+  if (!h->uploaded) return fail("hr_render: parameters not uploaded (call hr_upload)");
+  if (n == 0) return 0;
+  if (!rays || !rgb || !workspace) return fail("hr_render: null buffer");
+  if (ws_bytes < hr_workspace_bytes(h, n)) return fail("hr_render: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)hr_workspace_bytes(h, n));
+  if (((uintptr_t)workspace & 15) != 0) return fail("hr_render: workspace must be 16-byte aligned");
+  float* heads = (float*)workspace;
+  const hr_config& c = h->cfg;
+  EventPair em{nullptr, nullptr}, er{nullptr, nullptr};
+  const bool timing = h->timing && h->ev_render.size() < 8192;
+  if (timing) {
+    CK(cudaEventCreate(&em.a)); CK(cudaEventCreate(&em.b)); CK(cudaEventCreate(&er.a)); CK(cudaEventCreate(&er.b));
+    CK(cudaEventRecord(em.a, st));
+  }
+  cudaError_t e;
+  if (c.mlp_mode == HR_MLP_BF16X3_TC) {
+    if (!h->tc_ready) return fail("hr_render: tensor-core pack missing");
+    e = hr::launch_mlp_tc(c, h->tc, rays, heads, n, h->num_sms, st);
+  } else {
+    e = hr::launch_mlp_simt(c, h->simt, rays, heads, n, h->num_sms, st);
+  }
+  if (e != cudaSuccess) return fail("sample-net launch failed: %s", cudaGetErrorString(e));
+  if (timing) { CK(cudaEventRecord(em.b, st)); CK(cudaEventRecord(er.a, st)); }
+  e = hr::launch_render(c, h->dv, h->tabs, rays, heads, rgb, n, so, h->num_sms, st);
+  if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
+  if (timing) {
+    CK(cudaEventRecord(er.b, st));
+    h->ev_mlp.push_back(em);
+    h->ev_render.push_back(er);
+  }
+  h->launches += 2;
+  if (mlp_out) {
+    unpermute_heads<<<grid_for(n * (long long)c.mlp_out), 256, 0, st>>>(heads, mlp_out, n, c.n_samples, c.head_stride);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("unpermute launch failed: %s", cudaGetErrorString(e));
+    h->launches += 1;
+  }
+  return 0;
+}
+
+int hr_render(hr_handle* h, const float* rays, int64_t n_rays, float* rgb, void* workspace, int64_t workspace_bytes,
+              void* stream) {
+  if (h) CK(cudaSetDevice(h->device));
+  return render_impl(h, rays, n_rays, rgb, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int hr_render_stages(hr_handle* h, const float* rays, int64_t n_rays, float* rgb, float* mlp_out, float* distances,
+                     float* points, float* sigma, float* weights, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (h) CK(cudaSetDevice(h->device));
+  hr::StageOut so{distances, points, sigma, weights};
+  return render_impl(h, rays, n_rays, rgb, mlp_out, &so, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* rgb_host, int64_t chunk) {
+  if (!h) return fail("hr_render_host: null handle");
+  if (!h->uploaded) return fail("hr_render_host: parameters not uploaded");
+  if (n_rays == 0) return 0;
+  if (!rays_host || !rgb_host) return fail("hr_render_host: null buffer");
+  CK(cudaSetDevice(h->device));
+  if (chunk <= 0) chunk = 32768;
+  if (chunk > n_rays) chunk = n_rays;
+  HostPipe& P = h->pipe;
+  const hr_config& c = h->cfg;
+  if (P.chunk < chunk) {
+    for (int i = 0; i < 3; ++i) {
+      if (P.d_rays[i]) cudaFree(P.d_rays[i]);
+      if (P.d_rgb[i]) cudaFree(P.d_rgb[i]);
+      if (P.d_ws[i]) cudaFree(P.d_ws[i]);
+      P.d_rays[i] = P.d_rgb[i] = nullptr; P.d_ws[i] = nullptr;
+      if (!P.streams[i]) CK(cudaStreamCreateWithFlags(&P.streams[i], cudaStreamNonBlocking));
+    }
+    P.ws_bytes = hr_workspace_bytes(h, chunk);
+    for (int i = 0; i < 3; ++i) {
+      CK(cudaMalloc((void**)&P.d_rays[i], (size_t)chunk * c.c_in * sizeof(float)));
+      CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)chunk * 3 * sizeof(float)));
+      CK(cudaMalloc(&P.d_ws[i], (size_t)P.ws_bytes));
+    }
+    P.chunk = chunk;
+  }
+  int slot = 0;
+  for (int64_t off = 0; off < n_rays; off += chunk, slot = (slot + 1) % 3) {
+    int64_t m = (n_rays - off < chunk) ? (n_rays - off) : chunk;
+    cudaStream_t st = P.streams[slot];
+    CK(cudaMemcpyAsync(P.d_rays[slot], rays_host + off * c.c_in, (size_t)m * c.c_in * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = render_impl(h, P.d_rays[slot], m, P.d_rgb[slot], nullptr, nullptr, P.d_ws[slot], P.ws_bytes, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(rgb_host + off * 3, P.d_rgb[slot], (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < 3; ++i) CK(cudaStreamSynchronize(P.streams[i]));
+  return 0;
+}
+
+int64_t hr_launch_count(const hr_handle* h) { return h ? h->launches : -1; }
+
+int hr_timing_enable(hr_handle* h, int enable) {
+  if (!h) return fail("null handle");
+  h->timing = enable != 0;
+  return 0;
+}
+
+static void drop_events(std::vector<EventPair>& v) {
+  for (auto& p : v) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  v.clear();
+}
+
+int hr_timing_reset(hr_handle* h) {
+  if (!h) return fail("null handle");
+  drop_events(h->ev_render);
+  drop_events(h->ev_mlp);
+  return 0;
+}
+
+int hr_timing_read(hr_handle* h, double* render_ms_avg, double* mlp_ms_avg, int64_t* launches) {
+  if (!h) return fail("null handle");
+  double sr = 0, sm = 0;
+  for (auto& p : h->ev_render) {
+    CK(cudaEventSynchronize(p.b));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, p.a, p.b)); sr += ms;
+  }
+  for (auto& p : h->ev_mlp) {
+    CK(cudaEventSynchronize(p.b));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, p.a, p.b)); sm += ms;
+  }
+  size_t k = h->ev_render.size();
+  if (render_ms_avg) *render_ms_avg = k ? sr / k : 0.0;
+  if (mlp_ms_avg) *mlp_ms_avg = k ? sm / k : 0.0;
+  if (launches) *launches = (int64_t)k;
+  return 0;
+}
+
+int hr_destroy(hr_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  for (void* q : h->owned) cudaFree(q);
+  drop_events(h->ev_render);
+  drop_events(h->ev_mlp);
+  for (int i = 0; i < 3; ++i) {
+    if (h->pipe.d_rays[i]) cudaFree(h->pipe.d_rays[i]);
+    if (h->pipe.d_rgb[i]) cudaFree(h->pipe.d_rgb[i]);
+    if (h->pipe.d_ws[i]) cudaFree(h->pipe.d_ws[i]);
+    if (h->pipe.streams[i]) cudaStreamDestroy(h->pipe.streams[i]);
+  }
+  delete h;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// Shared device-side types for the hyperreel_b200 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hyperreel_b200.h"
+
+namespace hr {
+
+// One VM factor pair, channel-last (DESIGN.md "Data layout in HBM"):
+//   space  [H][W][C]   (reference [1,C,H,W]: x -> W (axis a), y -> H (axis b))
+//   second [H2][L][C]  dynamic: H2 = K keyframe rows, x -> L (axis c), y -> time
+//                      static : H2 = 1, the line [L][C]
+struct PlaneTab {
+  const float* space;
+  const float* second;
+  int H, W;   // space plane rows / cols
+  int H2, L;  // second factor rows / cols
+  int C;      // channels (0 = group absent, 4 or 8)
+};
+
+struct RenderTabs {
+  PlaneTab sig[3];
+  PlaneTab app[3];
+  const float* basis;  // [app_dim][sum C_app] row-major
+  int n_app_total;
+};
+
+// Host-derived scalars (computed in double on the host, then rounded once to fp32, the way the
+// reference's Python-float constants meet fp32 tensors).
+struct Derived {
+  float time_fac;       // K*(F-1)/F            (utils/flow_utils.py:19)
+  float time_inv_fac;   // 1/fac                (flow_utils.py:31)
+  float time_scale;     // (F-1)/F              (tensorf_dynamic.py:58)
+  float time_offset;    // 0.5/K                (tensorf_dynamic.py:59)
+  float kf_max;         // K-1
+  float inv_end_dist;   // contract_start_distance / contract_end_distance (contract.py:145)
+  float dist_scale_fac; // 1/(1-inv_end_dist)
+  float inv_end_rad;    // contract_start_radius / contract_end_radius (contract.py:184)
+  float rad_scale_fac;  // 1/(1-inv_end_rad)
+};
+
+// Optional per-sample dumps for stage-boundary parity tests (all may be null).
+struct StageOut {
+  float* distances;  // [n,S]
+  float* points;     // [n,S,3]
+  float* sigma;      // [n,S]
+  float* weights;    // [n,S]
+};
+
+__device__ __forceinline__ float apply_act(const hr_act& a, float x) {
+  // y = f(x*inner + shift) * outer, each op rounded separately like the eager reference.
+  float v = __fadd_rn(__fmul_rn(x, a.inner_fac), a.shift);
+  if (a.kind == HR_ACT_SIGMOID) {
+    v = 1.0f / (1.0f + expf(-v));
+  } else if (a.kind == HR_ACT_TANH) {
+    v = tanhf(v);
+  }
+  return __fmul_rn(v, a.outer_fac);
+}
+
+}  // namespace hr

@@ -1,0 +1,43 @@
+// Private definition of the opaque handle (shared by hr_api.cu and the weight packers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "hr_common.cuh"
+#include "hr_mlp.cuh"
+
+struct EventPair {
+  cudaEvent_t a, b;
+};
+
+struct HostPipe {
+  int64_t chunk = 0;
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  float* d_rays[3] = {nullptr, nullptr, nullptr};
+  float* d_rgb[3] = {nullptr, nullptr, nullptr};
+  void* d_ws[3] = {nullptr, nullptr, nullptr};
+  int64_t ws_bytes = 0;
+};
+
+struct hr_handle {
+  hr_config cfg;
+  hr::Derived dv;
+  int device = 0;
+  int num_sms = 148;
+  bool uploaded = false;
+  std::vector<void*> owned;  // device allocations of packed parameters
+  hr::RenderTabs tabs;
+  hr::MlpSimtPack simt;
+  hr::MlpTcPack tc;
+  bool tc_ready = false;
+  int64_t launches = 0;
+  bool timing = false;
+  std::vector<EventPair> ev_render, ev_mlp;
+  HostPipe pipe;
+};
+
+
+// error plumbing shared with the packers (sets hr_last_error, returns 1)
+int hr_fail(const char* fmt, ...);

@@ -1,0 +1,46 @@
+// Sample-net weight packs and launchers shared between hr_api.cu and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include "hyperreel_b200.h"
+
+namespace hr {
+
+// fp32 CUDA-core path: per layer a k-major matrix Wt[Kp][Np] (zero padded) and a bias[Np].
+//   layer 0      : rows = encoded input, padded to in_pad
+//   skip layer   : rows = [input (in_pad) ; hidden (W)]   (mlp.py:167-168: cat([input_x, x]))
+//   other layers : rows = hidden (W)
+//   last layer   : columns permuted to channel-major (column c*S+s  <-  reference row s*stride+c)
+struct MlpSimtPack {
+  const float* Wt[HR_MAX_LAYERS];
+  const float* bias[HR_MAX_LAYERS];
+  int Kp[HR_MAX_LAYERS];
+  int Np[HR_MAX_LAYERS];
+  int in_pad;
+  int n_layers;
+  int skip;
+};
+
+// tcgen05 path (HR_MLP_BF16X3_TC): see hr_mlp_tc.cu for the layout.
+struct MlpTcPack {
+  const void* wpack;        // bf16 hi/lo weight tiles, UMMA canonical layout
+  const float* bias[HR_MAX_LAYERS];
+  long long layer_off[HR_MAX_LAYERS];  // byte offset of each layer's tiles in wpack
+  int n_layers;
+  int skip;
+  int in_pad;
+  int n_out_pad;
+};
+
+size_t mlp_simt_smem_bytes(const MlpSimtPack& pk, int W);
+cudaError_t launch_mlp_simt(const hr_config& cfg, const MlpSimtPack& pk, const float* rays, float* heads,
+                            long long n, int num_sms, cudaStream_t stream);
+
+cudaError_t launch_mlp_tc(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
+                          int num_sms, cudaStream_t stream);
+}  // namespace hr
+
+struct hr_handle;
+struct hr_params;
+namespace hr {
+int pack_mlp_tc(hr_handle* h, const hr_params* p, const float* const* w_dev, const float* const* b_dev, cudaStream_t st);
+}

@@ -1,0 +1,248 @@
+"""``model_dict['lightfield']`` of the drop-in: the fused B200 light-field model.
+
+Mirrors the surface of the reference's ``LightfieldModel`` (nlf/models/models.py:104-143):
+``cls(cfg.model, system=...)``, ``forward(rays, render_kwargs) -> {'rgb': [N,3], ...}``,
+``embed(rays, render_kwargs)``, ``set_iter(i)``, attributes ``embedding_model`` / ``color_model.net``
+(with ``gridSize``, ``device``, ``init_svd_volume``, ``update_stepSize``, ``alphaMask`` as touched by
+``INRSystem.load_state_dict``, nlf/__init__.py:433-479).
+
+The whole graph RayParam -> RayPointEmbedding -> BaseColorModel is one native call
+(``hr_render``: sample-net kernel + fused intersect/gather/composite kernel); parameters are kept in
+reference-named ``nn.Parameter``s (state.py) and re-packed on the device whenever they change.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import lib as L
+from .signature import RENDER_ITER, Signature, UnsupportedPipeline, lower
+from .state import _Color, _Embedding, default_grid
+
+
+def _dataset_facts(system) -> dict:
+    """What reference constructors read from ``system`` (tensorf_dynamic.py:49-50, contract.py:121-125,
+    primitive.py:371-373, tensorf_no_sample.py:41-45)."""
+    if system is None:
+        return {}
+    if isinstance(system, dict):
+        return dict(system)
+    ds = {}
+    td = getattr(getattr(system, "dm", None), "train_dataset", None)
+    for k in ("num_keyframes", "num_frames", "near", "far", "depth_range"):
+        if td is not None and hasattr(td, k):
+            ds[k] = getattr(td, k)
+    dcfg = getattr(getattr(system, "cfg", None), "dataset", None)
+    if dcfg is not None:
+        for k in ("name", "collection"):
+            if k in dcfg:
+                ds[k] = dcfg[k]
+    return ds
+
+
+class LightfieldModel(nn.Module):
+    def __init__(self, cfg, **kwargs):
+        super().__init__()
+        dataset = kwargs.get("dataset") or _dataset_facts(kwargs.get("system"))
+        dataset.setdefault("near", 0.0)
+        dataset.setdefault("far", 1.0)
+        dataset.setdefault("depth_range", [dataset["near"], dataset["far"]])
+        mode = {"fp32": L.MLP_FP32_SIMT, "bf16x3": L.MLP_BF16X3_TC}[kwargs.get("mlp_mode", "fp32")]
+        self.cfg = cfg
+        self.sig: Signature = lower(cfg, dataset, cur_iter=RENDER_ITER,
+                                    iters_per_epoch=kwargs.get("iters_per_epoch"), mlp_mode=mode)
+        self.num_outputs = 3
+        self.cur_iter = RENDER_ITER
+        grid = kwargs.get("grid") or default_grid(self.sig)
+        # reference-named parameter storage
+        self.embedding_model = _Embedding(self.sig.mlp_layer_shapes)
+        self.color_model = _Color(self.sig, grid)
+        self._lib = L.load_library()  # raises if the CUDA library is missing -- no fallback
+        self._handle = C.c_void_p()
+        self._uploaded_version = None
+        self._device_index: Optional[int] = None
+        self._ws: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ reference surface
+    def set_iter(self, i):
+        """The fused path implements render-time semantics only (all PE windows open, EaseValue elapsed);
+        the reference sets iteration 1e7*iters when rendering (nlf/__init__.py:582-583)."""
+        self.cur_iter = i
+        lower(self.cfg, self.sig.dataset, cur_iter=int(i))  # raises UnsupportedPipeline if a window is still open
+        self.color_model.set_iter(i)
+
+    def forward(self, rays: torch.Tensor, render_kwargs: Optional[Dict] = None) -> Dict[str, torch.Tensor]:
+        render_kwargs = render_kwargs or {}
+        fields = list(render_kwargs.get("fields", []))
+        if self.training:
+            raise RuntimeError("hyperreel_b200.LightfieldModel implements the eval()/render path only; call .eval()")
+        rays = self._check_rays(rays)
+        n = rays.shape[0]
+        rgb = torch.empty((n, 3), device=rays.device, dtype=torch.float32)
+        if n == 0:
+            return {"rgb": rgb}
+        self._ensure_uploaded(rays.device)
+        ws = self._workspace(n, rays.device)
+        stream = torch.cuda.current_stream(rays.device).cuda_stream
+        if not fields:
+            L.check(self._lib.hr_render(self._handle, rays.data_ptr(), n, rgb.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+            return {"rgb": rgb}
+        # extra composited fields (tensorf_dynamic.py:813-837): weights -> 'render_weights', depth = sum w * distances
+        S = self.sig.n_samples
+        dist = torch.empty((n, S), device=rays.device)
+        wts = torch.empty((n, S), device=rays.device)
+        L.check(self._lib.hr_render_stages(self._handle, rays.data_ptr(), n, rgb.data_ptr(), None, dist.data_ptr(),
+                                           None, None, wts.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        out = {"rgb": rgb}
+        for key in fields:
+            if key == "render_weights":
+                out[key] = wts
+            elif key == "distances":
+                out[key] = (wts * dist).sum(-1, keepdim=True)
+            else:
+                raise UnsupportedPipeline(f"field '{key}' is not produced by the fused path")
+        return out
+
+    def embed(self, rays: torch.Tensor, render_kwargs: Optional[Dict] = None) -> Dict[str, torch.Tensor]:
+        """Per-sample outputs of the embedding pipeline, flattened per ray like RayPointEmbedding.forward
+        (nlf/embedding/embedding.py:112-114): 'points' [N, 3S], 'distances' [N, S]."""
+        st = self.render_stages(rays)
+        n = st["points"].shape[0]
+        return {"points": st["points"].reshape(n, -1), "distances": st["distances"].reshape(n, -1)}
+
+    # ------------------------------------------------------------------ native plumbing
+    def render_stages(self, rays: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Stage-boundary dump for parity bisecting (hr_render_stages)."""
+        rays = self._check_rays(rays)
+        n, S, c = rays.shape[0], self.sig.n_samples, self.sig.cfg
+        dev = rays.device
+        self._ensure_uploaded(dev)
+        out = {
+            "rgb": torch.empty((n, 3), device=dev), "mlp_out": torch.empty((n, c.mlp_out), device=dev),
+            "distances": torch.empty((n, S), device=dev), "points": torch.empty((n, S, 3), device=dev),
+            "sigma": torch.empty((n, S), device=dev), "weights": torch.empty((n, S), device=dev),
+        }
+        if n == 0:
+            return out
+        ws = self._workspace(n, dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        L.check(self._lib.hr_render_stages(self._handle, rays.data_ptr(), n, out["rgb"].data_ptr(), out["mlp_out"].data_ptr(),
+                                           out["distances"].data_ptr(), out["points"].data_ptr(), out["sigma"].data_ptr(),
+                                           out["weights"].data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        return out
+
+    def render_host(self, rays_host: torch.Tensor, rgb_host: Optional[torch.Tensor] = None, chunk: int = 0) -> torch.Tensor:
+        """Host-buffer entry (hr_render_host): pinned rays in, pinned rgb out, H2D/D2H overlapped inside."""
+        if rays_host.is_cuda or rays_host.dtype != torch.float32 or not rays_host.is_contiguous():
+            raise ValueError("render_host expects a contiguous fp32 host tensor")
+        if rays_host.shape[-1] != self.sig.c_in:
+            raise ValueError(f"rays must have {self.sig.c_in} channels")
+        n = rays_host.shape[0]
+        if rgb_host is None:
+            rgb_host = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
+        self._ensure_uploaded(torch.device("cuda", self._device_index if self._device_index is not None else torch.cuda.current_device()))
+        L.check(self._lib.hr_render_host(self._handle, rays_host.data_ptr(), n, rgb_host.data_ptr(), chunk))
+        return rgb_host
+
+    def timing(self, enable: bool = True):
+        L.check(self._lib.hr_timing_enable(self._handle, int(enable)))
+        L.check(self._lib.hr_timing_reset(self._handle))
+
+    def timing_read(self):
+        r, m, k = C.c_double(), C.c_double(), C.c_int64()
+        L.check(self._lib.hr_timing_read(self._handle, C.byref(r), C.byref(m), C.byref(k)))
+        return {"render_ms": r.value, "mlp_ms": m.value, "launches": k.value}
+
+    def launch_count(self) -> int:
+        return int(self._lib.hr_launch_count(self._handle)) if self._handle else 0
+
+    def mark_dirty(self):
+        """Call after mutating parameters in place (optimiser step, manual edits) so the next render re-packs."""
+        self._uploaded_version = None
+
+    def _check_rays(self, rays):
+        if not rays.is_cuda:
+            raise RuntimeError("hyperreel_b200 renders on a B200 only: rays must be a CUDA tensor (no CPU fallback)")
+        rays = rays.reshape(-1, rays.shape[-1])
+        if rays.shape[-1] != self.sig.c_in:
+            raise ValueError(f"rays must have {self.sig.c_in} channels, got {rays.shape[-1]}")
+        if rays.dtype != torch.float32:
+            raise ValueError("rays must be float32")
+        return rays.contiguous()
+
+    def _workspace(self, n, dev):
+        need = int(self._lib.hr_workspace_bytes(self._handle, n))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def _param_version(self):
+        return tuple((p._version, p.data_ptr()) for p in self.parameters()) + tuple(self.color_model.net.gridSize.tolist())
+
+    def _ensure_uploaded(self, dev: torch.device):
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        # aabb is checkpoint state (it changes when the reference shrinks the grid, tensorf_base.py:1190-1232)
+        aabb = [float(v) for v in self.color_model.net.aabb.detach().cpu().reshape(-1).tolist()]
+        if aabb != [float(self.sig.cfg.aabb[i]) for i in range(6)]:
+            for i in range(6):
+                self.sig.cfg.aabb[i] = aabb[i]
+            if self._handle:
+                self._lib.hr_destroy(self._handle)
+                self._handle = C.c_void_p()
+        if not self._handle or self._device_index != idx:
+            if self._handle:
+                self._lib.hr_destroy(self._handle)
+                self._handle = C.c_void_p()
+            L.check(self._lib.hr_create(C.byref(self.sig.cfg), idx, C.byref(self._handle)))
+            self._device_index = idx
+            self._uploaded_version = None
+        ver = self._param_version()
+        if self._uploaded_version == ver:
+            return
+        P = L.hr_params()
+        keep = []  # keep tensors alive until the upload has been enqueued and synchronised
+
+        def dptr(t):
+            t = t.detach()
+            if not t.is_cuda or t.device.index != idx:
+                t = t.to(torch.device("cuda", idx))
+            t = t.contiguous().float()
+            keep.append(t)
+            return t.data_ptr()
+
+        P.on_device = 1
+        net = self.embedding_model.embeddings[0].net
+        for i, layer in enumerate(net.layers):
+            lin = layer[0] if isinstance(layer, nn.Sequential) else layer
+            P.mlp_weight[i] = dptr(lin.weight)
+            P.mlp_bias[i] = dptr(lin.bias)
+        tn = self.color_model.net
+        dplane, dsecond, aplane, asecond = tn.tables()
+        for i in range(3):
+            C_i = dplane[i].shape[1]
+            P.plane_h[i], P.plane_w[i] = dplane[i].shape[2], dplane[i].shape[3]
+            P.second_len[i] = dsecond[i].shape[3] if tn.dynamic else dsecond[i].shape[2]
+            if C_i > 0:
+                P.sigma_plane[i], P.app_plane[i] = dptr(dplane[i]), dptr(aplane[i])
+                P.sigma_second[i], P.app_second[i] = dptr(dsecond[i]), dptr(asecond[i])
+        P.basis_mat = dptr(tn.basis_mat.weight)
+        stream = torch.cuda.current_stream(torch.device("cuda", idx))
+        L.check(self._lib.hr_upload(self._handle, C.byref(P), stream.cuda_stream))
+        stream.synchronize()
+        self._uploaded_version = ver
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._lib.hr_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+
+model_dict = {"lightfield": LightfieldModel}
+ray_model_dict = {"lightfield": LightfieldModel}
+pos_model_dict = {"lightfield": LightfieldModel}

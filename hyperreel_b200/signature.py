@@ -1,0 +1,406 @@
+"""Recognise the pipeline a model config describes and lower it to the C-ABI ``hr_config``.
+
+The reference builds an arbitrary graph from the YAML (ordered embeddings over a dict of named
+per-sample fields).  The fused CUDA path implements one family of graphs:
+
+    ray_prediction -> ray_intersect(z_plane | sphere) -> [advect_points] -> [point_offset]
+                   -> add_point_outputs -> extract_fields -> tensor_vm_split_time | tensor_vm_split_no_sample
+
+Anything else raises ``UnsupportedPipeline`` at construction -- there is no fallback path.
+Host-side constants are computed with the same torch ops the reference's constructors use
+(``torch.linspace`` for the base primitives, nlf/intersect/z.py:50-71).
+"""
+from __future__ import annotations
+
+import copy
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import lib as L
+from .config import Cfg, to_cfg
+
+
+class UnsupportedPipeline(NotImplementedError):
+    pass
+
+
+def _get(cfg, key, default=None):
+    return cfg[key] if (cfg is not None and key in cfg) else default
+
+
+RENDER_ITER = 10_000_000  # what the reference sets when rendering (nlf/__init__.py:582-583)
+
+
+def resolve_activation(cfg, cur_iter: int = RENDER_ITER) -> L.hr_act:
+    """get_activation (nlf/activations.py:566-570) lowered to y = f(x*inner+shift)*outer.
+    EaseValue (:462-496) is accepted only once its window has elapsed (then it is its inner activation)."""
+    if cfg is None:
+        cfg = {"type": "identity"}
+    if isinstance(cfg, str):
+        cfg = {"type": cfg}
+    t = cfg["type"]
+    if t == "ease_value":
+        wait = _get(cfg, "wait_iters", 0.0)
+        window = _get(cfg, "window_iters", 0.0)
+        if (cur_iter - wait) < window:
+            raise UnsupportedPipeline(f"ease_value window still open at iteration {cur_iter} (render-time config expected)")
+        return resolve_activation(cfg["activation"], cur_iter)
+    kinds = {"identity": L.ACT_IDENTITY, "sigmoid": L.ACT_SIGMOID, "tanh": L.ACT_TANH}
+    if t not in kinds:
+        raise UnsupportedPipeline(f"activation '{t}' is not on the fused path")
+    outer = _get(cfg, "outer_fac", 1.0)
+    if "fac" in cfg:
+        outer = cfg["fac"]
+    return L.hr_act(kinds[t], float(_get(cfg, "inner_fac", 1.0)), float(_get(cfg, "shift", 0.0)), float(outer))
+
+
+# ---- mipnerf distance contraction on the host (nlf/contract.py:160-176), used for the base primitives ----
+def _contract_distance(distance: torch.Tensor, start_distance: float, end_distance: float) -> torch.Tensor:
+    distance = distance / start_distance
+    inverse_distance = 1.0 / torch.abs(distance)
+    inv_end = start_distance / end_distance
+    scale = 1.0 / (1.0 - inv_end)
+    t = (inverse_distance - inv_end) * scale
+    distance = torch.where(torch.abs(distance) < 1.0, distance / 1.0, torch.sign(distance) * (2.0 - t))
+    return (distance / 2.0) * 2.0
+
+
+HEAD_ROLES = ("z_vals", "spatial_flow", "sigma", "point_sigma", "point_offset", "color_scale", "color_shift")
+
+
+@dataclass
+class Signature:
+    """Everything the host needs to know about a recognised pipeline."""
+    cfg: L.hr_config
+    model_cfg: Cfg
+    dataset: dict
+    head_names: List[str] = field(default_factory=list)
+    head_channels: List[int] = field(default_factory=list)
+    mlp_layer_shapes: List[tuple] = field(default_factory=list)  # (out, in) per Linear
+    dynamic: bool = False
+
+    @property
+    def c_in(self) -> int:
+        return self.cfg.c_in
+
+    @property
+    def n_samples(self) -> int:
+        return self.cfg.n_samples
+
+
+def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch: Optional[int] = None,
+          mlp_mode: int = L.MLP_FP32_SIMT) -> Signature:
+    """model cfg (reference schema) + dataset facts -> Signature / hr_config."""
+    from .config import epochs_to_iters
+
+    m = to_cfg(copy.deepcopy(dict(model_cfg)))
+    if iters_per_epoch is not None:
+        epochs_to_iters(m, iters_per_epoch)
+    else:
+        epochs_to_iters(m, 1)  # render-time: any positive scale; windows are checked against cur_iter
+    ds = dict(dataset)
+    c = L.hr_config()
+    c.abi_version = L.HR_ABI_VERSION
+    c.mlp_mode = int(mlp_mode)
+
+    if m.type != "lightfield" or m.render.type != "lightfield":
+        raise UnsupportedPipeline("only model/render type 'lightfield'")
+    if _get(m.param, "fn", "identity") != "identity":
+        raise UnsupportedPipeline("top-level ray param must be identity")
+    if "subdivision" in m and _get(m.subdivision, "type") is not None:
+        raise UnsupportedPipeline("subdivision is not on the fused path")
+    if m.embedding.type != "ray_point":
+        raise UnsupportedPipeline("embedding type must be ray_point")
+
+    embs = m.embedding.embeddings
+    seq = []
+    for key in embs.keys():
+        e = embs[key]
+        wait = _get(e, "wait_iters", 0)
+        stop = _get(e, "stop_iters", float("inf"))
+        if cur_iter >= wait and cur_iter < stop:  # RayPointEmbedding.forward gate (embedding.py:107)
+            seq.append(e)
+    types = [e.type for e in seq]
+    expect = ["ray_prediction", "ray_intersect"]
+    rest = types[2:]
+    allowed_tail = [t for t in ("advect_points", "point_offset", "add_point_outputs", "extract_fields") if t in rest]
+    if types[:2] != expect or rest != allowed_tail or "add_point_outputs" not in rest or "extract_fields" not in rest:
+        raise UnsupportedPipeline(f"embedding sequence {types} is not a recognised pipeline")
+    pred, isect = seq[0], seq[1]
+    flow = next((e for e in seq if e.type == "advect_points"), None)
+    offset = next((e for e in seq if e.type == "point_offset"), None)
+    addp = next(e for e in seq if e.type == "add_point_outputs")
+    extract = next(e for e in seq if e.type == "extract_fields")
+
+    net = m.color.net
+    if m.color.type != "base" or net.type not in ("tensor_vm_split_time", "tensor_vm_split_no_sample"):
+        raise UnsupportedPipeline(f"colour net '{net.type}' is not on the fused path")
+    dynamic = net.type == "tensor_vm_split_time"
+
+    # ------------------------------------------------------------------ sample-net input (ray.py:235-263)
+    max_end = 6
+    groups = []
+    mlp_in = 0
+    for key in pred.params.keys():
+        p = pred.params[key]
+        g = L.hr_encode_group()
+        g.start, g.end = int(p.start), int(p.end)
+        max_end = max(max_end, g.end)
+        fn = p.param.fn
+        if fn == "identity":
+            g.fn, dims = L.PARAM_IDENTITY, g.end - g.start
+        elif fn == "two_plane":
+            g.fn, dims = L.PARAM_TWO_PLANE, 4
+            if any(k in p.param for k in ("origin", "use_local_param")) or g.end - g.start != 6:
+                raise UnsupportedPipeline("two_plane: origin/local param not supported")
+        elif fn == "pluecker":
+            g.fn, dims = L.PARAM_PLUECKER, 6
+            if any(k in p.param for k in ("origin", "use_local_param")) or g.end - g.start != 6:
+                raise UnsupportedPipeline("pluecker: origin/local param not supported")
+        else:
+            raise UnsupportedPipeline(f"ray param '{fn}' is not on the fused path")
+        if dims > 8:
+            raise UnsupportedPipeline("param group wider than 8 channels")
+        g.near, g.far = float(_get(p.param, "near", -1.0)), float(_get(p.param, "far", 0.0))
+        g.dir_mult = float(_get(p.param, "direction_multiplier", 1.0))
+        g.mom_mult = float(_get(p.param, "moment_multiplier", 1.0))
+        pe = _get(p, "pe")
+        g.n_freqs, g.exclude_identity, g.freq_mult, g.base_mult = 0, 0, 2.0, 1.0
+        if pe is not None:
+            if pe.type != "windowed":
+                raise UnsupportedPipeline(f"pe type '{pe.type}' is not on the fused path")
+            # all windows must be open (pe.py:186-196): cur_iter past wait and past max_freq_iter
+            mfi = float(_get(pe, "max_freq_iter", 0))
+            if "window_iters" in pe:
+                mfi = max(max(w) for w in pe.window_iters)
+            if (cur_iter - _get(pe, "wait_iters", 0)) < 0 or (mfi != 0 and not cur_iter > mfi):
+                raise UnsupportedPipeline("windowed PE not fully open at this iteration")
+            if _get(pe, "ceil", False) or _get(pe, "window_identity", False):
+                pass  # irrelevant once every weight is 1
+            g.n_freqs = int(pe.n_freqs)
+            g.exclude_identity = int(bool(_get(pe, "exclude_identity", False)))
+            g.freq_mult = float(_get(pe, "freq_multiplier", 2.0))
+            g.base_mult = float(_get(pe, "base_multiplier", 1.0))
+        mlp_in += dims * (2 * g.n_freqs + (0 if g.exclude_identity else 1))
+        groups.append(g)
+    if len(groups) > L.HR_MAX_GROUPS:
+        raise UnsupportedPipeline("too many param groups")
+    c.n_groups = len(groups)
+    for i, g in enumerate(groups):
+        c.groups[i] = g
+    c.c_in = 8 if (dynamic or flow is not None or max_end > 6) else 6
+    if max_end > c.c_in:
+        raise UnsupportedPipeline("param group reads beyond the ray")
+
+    # ------------------------------------------------------------------ sample net (mlp.py:60-178)
+    ncfg = pred.net
+    if ncfg.type != "base":
+        raise UnsupportedPipeline(f"sample net '{ncfg.type}' is not on the fused path")
+    for k in ("pe", "latent_dim", "pad_to", "is_constant", "zero_before_channel", "pe_channels"):
+        if k in ncfg:
+            raise UnsupportedPipeline(f"sample net option '{k}' is not on the fused path")
+    if _get(ncfg, "activation", "identity") != "identity" or _get(ncfg, "layer_activation", "leaky_relu") != "leaky_relu":
+        raise UnsupportedPipeline("sample net activations must be leaky_relu / identity")
+    if not _get(ncfg, "bias", True):
+        raise UnsupportedPipeline("bias-free sample net")
+    depth = int(ncfg.depth)  # RayPredictionEmbedding: depth -= 2, linear_last=False -> `depth` Linear layers
+    skips = list(_get(ncfg, "skips", []))
+    if len(skips) > 1:
+        raise UnsupportedPipeline("more than one skip connection")
+    S = int(pred.z_channels)
+    if int(isect.z_channels) != S:
+        raise UnsupportedPipeline("z_channels mismatch between prediction and intersection")
+    if "ray_outputs" in pred and len(pred.ray_outputs) > 0:
+        raise UnsupportedPipeline("per-ray outputs are not on the fused path")
+    head_names = list(pred.outputs.keys())
+    head_channels = [int(pred.outputs[k].channels) for k in head_names]
+    stride = sum(head_channels)
+    c.mlp_in, c.mlp_width, c.mlp_layers = mlp_in, int(ncfg.hidden_channels), depth
+    c.mlp_skip = int(skips[0]) if skips else -1
+    c.mlp_out = S * stride
+    c.leaky_slope = 0.01
+    c.n_samples, c.head_stride = S, stride
+    W = c.mlp_width
+    shapes = []
+    for i in range(depth):
+        fin = mlp_in if i == 0 else (W + mlp_in if i == c.mlp_skip else W)
+        fout = c.mlp_out if i == depth - 1 else W
+        shapes.append((fout, fin))
+
+    # ------------------------------------------------------------------ heads (ray.py:331-337)
+    offs: Dict[str, int] = {}
+    o = 0
+    for nme, ch in zip(head_names, head_channels):
+        if nme not in HEAD_ROLES:
+            raise UnsupportedPipeline(f"head '{nme}' is not on the fused path")
+        offs[nme] = o
+        o += ch
+    expect_ch = {"spatial_flow": 3, "sigma": 1, "point_sigma": 1, "point_offset": 3, "color_scale": 3, "color_shift": 3}
+    for nme, ch in zip(head_names, head_channels):
+        if nme in expect_ch and ch != expect_ch[nme]:
+            raise UnsupportedPipeline(f"head '{nme}' must have {expect_ch[nme]} channels")
+
+    def act_of(nme):
+        return resolve_activation(_get(pred.outputs[nme], "activation"), cur_iter) if nme in offs else L.hr_act(0, 1.0, 0.0, 1.0)
+
+    c.off_z = offs.get("z_vals", -1)
+    c.n_z = head_channels[head_names.index("z_vals")] if "z_vals" in offs else 0
+    c.off_flow, c.off_sigma = offs.get("spatial_flow", -1), offs.get("sigma", -1)
+    c.off_point_sigma, c.off_offset = offs.get("point_sigma", -1), offs.get("point_offset", -1)
+    c.off_cscale, c.off_cshift = offs.get("color_scale", -1), offs.get("color_shift", -1)
+    c.act_z, c.act_flow, c.act_sigma = act_of("z_vals"), act_of("spatial_flow"), act_of("sigma")
+    c.act_point_sigma, c.act_offset = act_of("point_sigma"), act_of("point_offset")
+    c.act_cscale, c.act_cshift = act_of("color_scale"), act_of("color_shift")
+
+    # ------------------------------------------------------------------ intersection (base.py:52-126, z.py, primitive.py)
+    it = isect.intersect
+    for k in ("origin", "weight_fn", "sort_outputs", "mask", "dropout", "num_repeat", "z_scale",
+              "num_samples_for_scale", "use_local_prediction", "flip_axes"):
+        if k in it and it[k] not in (False, None, 1):
+            raise UnsupportedPipeline(f"intersect option '{k}' is not on the fused path")
+    for k in ("use_disparity", "residual_z", "residual_distance", "normalize", "clamp", "forward_facing", "max_axis",
+              "outward_facing"):
+        if _get(it, k, False):
+            raise UnsupportedPipeline(f"intersect option '{k}' is not on the fused path")
+    if _get(isect, "rays_name", "rays") != "rays":
+        raise UnsupportedPipeline("rays_name override")
+    use_ds = bool(_get(it, "use_dataset_bounds", False))
+    contract = _get(it, "contract")
+    c.contract_type, c.contract_samples = L.CONTRACT_NONE, 0
+    c.contract_start_radius = c.contract_start_distance = 1.0
+    c.contract_end_radius = c.contract_end_distance = float("inf")
+    if contract is not None and contract.type != "identity":
+        if contract.type != "mipnerf":
+            raise UnsupportedPipeline(f"contract '{contract.type}' is not on the fused path")
+        if "distance_activation" in contract or "stop_iters" in contract:
+            raise UnsupportedPipeline("contract distance_activation / stop_iters")
+        if _get(contract, "use_dataset_bounds", False):  # contract.py:121-125
+            sr = _get(contract, "contract_start_radius", max(ds["depth_range"][0] * 1.5, 1.0))
+            er = _get(contract, "contract_end_radius", ds["depth_range"][1] * 1.5)
+        else:
+            sr = _get(contract, "contract_start_radius", 1.0)
+            er = _get(contract, "contract_end_radius", float("inf"))
+        c.contract_type = L.CONTRACT_MIPNERF
+        c.contract_samples = int(bool(_get(contract, "contract_samples", False)))
+        c.contract_start_radius, c.contract_end_radius = float(sr), float(er)
+        c.contract_start_distance = float(_get(contract, "contract_start_distance", sr))
+        c.contract_end_distance = float(_get(contract, "contract_end_distance", er))
+    if it.type == "z_plane":
+        c.isect_type = L.ISECT_Z_PLANE
+        if use_ds:  # z.py:26-31
+            initial, end = torch.tensor(-ds["near"]), torch.tensor(-ds["far"])
+        else:
+            initial, end = torch.tensor(_get(it, "initial", 0.0)), torch.tensor(_get(it, "end", 1.0))
+    elif it.type == "sphere":
+        c.isect_type = L.ISECT_SPHERE
+        if use_ds:  # primitive.py:371-376
+            initial = torch.tensor(_get(it, "initial", ds["near"] * 1.5))
+            end = torch.tensor(_get(it, "end", ds["far"] * 1.5))
+        else:
+            initial, end = torch.tensor(_get(it, "initial", 0.0)), torch.tensor(_get(it, "end", 1.0))
+        oi = _get(it, "origin_initial", [1.0, 1.0, 1.0])
+        for i in range(3):
+            c.sphere_origin_initial[i] = float(oi[i])
+        c.sphere_origin_scale = float(_get(it, "origin_scale_factor", 0.0))
+    else:
+        raise UnsupportedPipeline(f"intersect '{it.type}' is not on the fused path")
+    initial, end = initial.float(), end.float()
+    if c.contract_samples:
+        initial = _contract_distance(initial, c.contract_start_distance, c.contract_end_distance)
+        end = _contract_distance(end, c.contract_start_distance, c.contract_end_distance)
+    if S > L.HR_MAX_SAMPLES:
+        raise UnsupportedPipeline(f"z_channels {S} > {L.HR_MAX_SAMPLES}")
+    samples = torch.linspace(float(initial), float(end), S)
+    for i in range(S):
+        c.samples[i] = float(samples[i])
+    c.z_scale = float(torch.abs(samples[1] - samples[0])) if S > 1 else 1.0
+    c.isect_near = float(_get(it, "near", ds["near"] if use_ds else 0.0))
+    c.isect_far = float(_get(it, "far", float("inf")))
+    c.isect_sort = int(bool(_get(it, "sort", False)))
+    c.isect_act = resolve_activation(_get(it, "activation", "identity"), cur_iter)
+    c.isect_use_sigma = int(bool(_get(it, "use_sigma", False)))
+    c.isect_density_off = offs.get(_get(it, "in_density_field", "sigma"), -1)
+    if c.isect_density_off not in (-1, c.off_sigma, c.off_point_sigma):
+        raise UnsupportedPipeline("intersect density field must be sigma or point_sigma")
+
+    # ------------------------------------------------------------------ flow (point.py:741-831)
+    c.num_keyframes, c.num_frames = int(ds.get("num_keyframes", 1)), int(ds.get("num_frames", 1))
+    c.use_flow = 0
+    c.flow_act = L.hr_act(0, 1.0, 0.0, 1.0)
+    if flow is not None:
+        if _get(flow, "use_angular_flow", False):
+            raise UnsupportedPipeline("angular flow is not on the fused path")
+        for k in ("rays_name", "in_points_field", "out_points_field"):
+            if k in flow:
+                raise UnsupportedPipeline(f"advect_points option '{k}'")
+        if _get(flow, "use_spatial_flow", False):
+            if "spatial_flow" not in offs:
+                raise UnsupportedPipeline("spatial flow without a spatial_flow head")
+            c.use_flow = 1
+            c.flow_act = resolve_activation(_get(flow, "spatial_flow_activation", "identity"), cur_iter)
+
+    # ------------------------------------------------------------------ point offset (point.py:338-399)
+    c.use_offset, c.offset_density_off = 0, -1
+    c.offset_act = L.hr_act(0, 1.0, 0.0, 1.0)
+    if offset is not None:
+        for k in ("in_offset_field", "in_points_field", "out_points_field", "dropout"):
+            if k in offset:
+                raise UnsupportedPipeline(f"point_offset option '{k}'")
+        if "point_offset" not in offs:
+            raise UnsupportedPipeline("point_offset without a point_offset head")
+        c.use_offset = 1
+        if _get(offset, "use_sigma", True):
+            c.offset_density_off = offs.get(_get(offset, "in_density_field", "sigma"), -1)
+        c.offset_act = resolve_activation(_get(offset, "activation", "identity"), cur_iter)
+
+    # ------------------------------------------------------------------ outputs to the colour net
+    extras = list(addp.extra_outputs)
+    fields = list(extract.fields)
+    for need in ("points", "distances", "viewdirs", "weights"):
+        if need not in fields:
+            raise UnsupportedPipeline(f"extract_fields must pass '{need}'")
+    if "viewdirs" not in extras:
+        raise UnsupportedPipeline("add_point_outputs must add viewdirs")
+    if dynamic and (flow is None or not all(f in fields for f in ("base_times", "times", "time_offset")) or "times" not in extras):
+        raise UnsupportedPipeline("dynamic colour net needs advect_points + time fields")
+    if "color_transform" in offs or "color_scale_global" in offs:
+        raise UnsupportedPipeline("colour transform heads are not on the fused path")
+    c.use_color_scale_shift = int("color_scale" in offs and "color_scale" in fields and "color_shift" in offs and "color_shift" in fields)
+    if ("color_scale" in offs and "color_scale" in fields) != ("color_shift" in offs and "color_shift" in fields):
+        raise UnsupportedPipeline("color_scale and color_shift must come together")
+
+    # ------------------------------------------------------------------ TensoRF decode (tensorf_base.py:138-260)
+    c.dynamic = int(dynamic)
+    aabb = net.aabb
+    for i in range(3):
+        c.aabb[i], c.aabb[3 + i] = float(aabb[0][i]), float(aabb[1][i])
+    c.distance_scale = float(_get(net, "distance_scale", 25))
+    ns, na = list(_get(net, "n_lamb_sigma", [8])), list(_get(net, "n_lamb_sh", [24]))
+    if len(ns) != 3 or len(na) != 3:
+        raise UnsupportedPipeline("n_lamb_sigma / n_lamb_sh must have 3 entries")
+    for i in range(3):
+        c.n_sigma[i], c.n_app[i] = int(ns[i]), int(na[i])
+    c.app_dim = int(_get(net, "data_dim_color", 27))
+    mode = _get(net, "shadingMode", "MLP_PE")
+    if mode == "SH":
+        c.shading = L.SHADE_SH
+    elif mode == "RGB":
+        c.shading = L.SHADE_RGB
+    else:
+        raise UnsupportedPipeline(f"shadingMode '{mode}' is not on the fused path")
+    if dynamic and _get(net, "densityMode", "Density") != "Density":
+        raise UnsupportedPipeline("densityMode must be Density")
+    if "filter" in net and len(net.filter) > 0:
+        raise UnsupportedPipeline("weight filtering is not on the fused path")
+    c.white_bg = int(bool(_get(net, "white_bg", 0)) or (not dynamic and ds.get("name") == "blender"))
+    c.black_bg = int(bool(_get(net, "black_bg", 0)) or (not dynamic and ds.get("collection") == "bulldozer"))
+    c.weight_thre = float(_get(net, "rm_weight_mask_thre", 0.0001))
+    act = _get(net, "fea2denseAct", "softplus")
+    c.fea2dense = {"relu": L.DENSE_RELU, "softplus": L.DENSE_SOFTPLUS, "relu_abs": L.DENSE_RELU_ABS}[act]
+    c.density_shift = float(_get(net, "density_shift", -10.0))
+    c.clamp_output = 1
+    return Signature(cfg=c, model_cfg=m, dataset=ds, head_names=head_names, head_channels=head_channels,
+                     mlp_layer_shapes=shapes, dynamic=dynamic)

@@ -1,0 +1,155 @@
+"""Parameter containers with the reference's ``state_dict`` names, and reference-style initialisers.
+
+The fused model keeps its parameters in ordinary ``nn.Parameter``s laid out exactly like the reference
+modules, so a Lightning checkpoint of the reference loads with
+``load_state_dict`` -- only the *storage* lives here; no torch op ever runs on them on the render path
+(the native library packs them into its own device layout on upload).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from .signature import Signature
+
+MAT_MODE = [[0, 1], [0, 2], [1, 2]]  # tensorf_base.py:231, tensorf_dynamic.py:47
+VEC_MODE = [2, 1, 0]                 # tensorf_base.py:232; time planes pair axis c with time (tensorf_dynamic.py:48)
+
+
+def n_to_reso(n_voxels: int, aabb: torch.Tensor) -> List[int]:
+    """utils/tensorf_utils.py:65-68 (fp32 tensor arithmetic, truncating)."""
+    xyz_min, xyz_max = aabb[0].float(), aabb[1].float()
+    voxel_size = ((xyz_max - xyz_min).prod() / n_voxels).pow(1 / 3)
+    return ((xyz_max - xyz_min) / voxel_size).long().tolist()
+
+
+class _SampleNet(nn.Module):
+    """Storage twin of BaseMLP (nlf/nets/mlp.py:127-154): layers.{i}.0.{weight,bias}, last layers.{L-1}.{...}."""
+
+    def __init__(self, shapes: Sequence[tuple]):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        for i, (fout, fin) in enumerate(shapes):
+            lin = nn.Linear(fin, fout)  # PyTorch default init == reference (weight_init: none)
+            self.layers.append(lin if i == len(shapes) - 1 else nn.Sequential(lin, nn.LeakyReLU(0.01)))
+
+
+class _Prediction(nn.Module):
+    def __init__(self, shapes):
+        super().__init__()
+        self.net = _SampleNet(shapes)
+
+
+class _Embedding(nn.Module):
+    def __init__(self, shapes):
+        super().__init__()
+        self.embeddings = nn.ModuleList([_Prediction(shapes)])
+
+
+class _Tensorf(nn.Module):
+    """Storage twin of TensorVMKeyframeTime / TensorVMNoSample parameters (tensorf_dynamic.py:106-244,
+    tensorf_base.py:895-991)."""
+
+    def __init__(self, sig: Signature, grid: Sequence[int]):
+        super().__init__()
+        c = sig.cfg
+        self.dynamic = bool(c.dynamic)
+        self.register_buffer("aabb", torch.tensor([[c.aabb[0], c.aabb[1], c.aabb[2]], [c.aabb[3], c.aabb[4], c.aabb[5]]]))
+        self.register_buffer("gridSize", torch.tensor(list(grid), dtype=torch.long))
+        self.n_sigma = [int(c.n_sigma[i]) for i in range(3)]
+        self.n_app = [int(c.n_app[i]) for i in range(3)]
+        self.K = int(c.num_keyframes)
+        self.basis_mat = nn.Linear(sum(self.n_app), int(c.app_dim), bias=False)
+        if self.dynamic:
+            self.basis_mat_density = nn.Linear(sum(self.n_sigma), 1, bias=False)
+        self.alphaMask = None
+        self.device = "cuda"
+        self.init_svd_volume(None, None)
+
+    def _shapes(self, comps, i, grid):
+        a, b = MAT_MODE[i]
+        v = VEC_MODE[i]
+        plane = (1, comps[i], int(grid[b]), int(grid[a]))
+        second = (1, comps[i], self.K, int(grid[v])) if self.dynamic else (1, comps[i], int(grid[v]), 1)
+        return plane, second
+
+    def init_svd_volume(self, res, device):
+        """Re-create the tables at ``self.gridSize`` (reference: nlf/__init__.py:448-454 calls this before
+        loading a checkpoint whose grids were up-sampled/shrunk)."""
+        grid = self.gridSize.tolist()
+        names = (("density_plane_space", "density_plane_time", "app_plane_space", "app_plane_time") if self.dynamic
+                 else ("density_plane", "density_line", "app_plane", "app_line"))
+        dp, d2, ap, a2 = [], [], [], []
+        for i in range(3):
+            ps, ss = self._shapes(self.n_sigma, i, grid)
+            pa, sa = self._shapes(self.n_app, i, grid)
+            # density: 1e-2 * U(0,1).clamp(1e-2, 1e8)  (fea2denseAct relu); appearance: 0.1 * N(0,1)
+            dp.append(nn.Parameter(1e-2 * torch.rand(ps).clamp(1e-2, 1e8)))
+            d2.append(nn.Parameter(1e-2 * torch.rand(ss).clamp(1e-2, 1e8)))
+            ap.append(nn.Parameter(0.1 * torch.randn(pa)))
+            a2.append(nn.Parameter(0.1 * torch.randn(sa)))
+        setattr(self, names[0], nn.ParameterList(dp))
+        setattr(self, names[1], nn.ParameterList(d2))
+        setattr(self, names[2], nn.ParameterList(ap))
+        setattr(self, names[3], nn.ParameterList(a2))
+
+    def update_stepSize(self, gridSize):
+        self.gridSize = torch.as_tensor(gridSize, dtype=torch.long)
+
+    def tables(self):
+        if self.dynamic:
+            return self.density_plane_space, self.density_plane_time, self.app_plane_space, self.app_plane_time
+        return self.density_plane, self.density_line, self.app_plane, self.app_line
+
+    def set_iter(self, i):
+        self.cur_iter = i
+
+
+class _Color(nn.Module):
+    def __init__(self, sig, grid):
+        super().__init__()
+        self.net = _Tensorf(sig, grid)
+
+    def set_iter(self, i):
+        self.net.set_iter(i)
+
+
+def default_grid(sig: Signature) -> List[int]:
+    """Initial grid of the reference constructor: N_to_reso(N_voxel_init, aabb) (tensorf_base.py:156-159)."""
+    net = sig.model_cfg.color.net
+    if "grid_size" in net:
+        return list(net.grid_size.start)
+    return n_to_reso(int(net.N_voxel_init), torch.tensor(net.aabb))
+
+
+def scale_density(sd: Dict[str, torch.Tensor], gain: float) -> Dict[str, torch.Tensor]:
+    """"Trained-like" variant: scale the sigma space planes so transmittance
+    saturates along a ray instead of leaving every sample nearly transparent."""
+    out = {}
+    for k, v in sd.items():
+        if ("density_plane" in k) and ("time" not in k):
+            out[k] = v * gain
+        else:
+            out[k] = v
+    return out
+
+
+def seeded_state_dict(sig: Signature, grid: Optional[Sequence[int]] = None, seed: int = 0, density_gain: float = 1.0,
+                      prefix: str = "model.") -> Dict[str, torch.Tensor]:
+    """Reference-style random initialisation of every parameter, deterministic in ``seed`` (CPU generator),
+    keyed like ``RenderLightfield.state_dict()`` (``model.embedding_model...``, ``model.color_model.net...``)."""
+    grid = list(grid) if grid is not None else default_grid(sig)
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)
+        emb = _Embedding(sig.mlp_layer_shapes)
+        col = _Color(sig, grid)
+    sd = {}
+    for k, v in emb.state_dict().items():
+        sd[f"{prefix}embedding_model.{k}"] = v.detach().clone()
+    for k, v in col.state_dict().items():
+        sd[f"{prefix}color_model.{k}"] = v.detach().clone()
+    if density_gain != 1.0:
+        sd = scale_density(sd, density_gain)
+    return sd

@@ -1,0 +1,212 @@
+/*
+ * hyperreel_b200 -- C-ABI of the B200-native HyperReel per-ray rendering hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference has no
+ * FFI (it is pure PyTorch); every entry point below names the reference interface it replaces
+ * (file:line under the reference checkout).  The Python binding a maintainer would add is the ctypes
+ * stub shown in INTEGRATION.md (hyperreel_b200/lib.py is that stub, complete).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; hr_last_error() gives the message
+ *     (the reference raises Python exceptions / asserts: nlf/nets/tensorf_dynamic.py:744-745;
+ *     the Python shim turns a non-zero status into RuntimeError);
+ *   - all work is enqueued on the caller's cudaStream_t (passed as void*): the reference runs on
+ *     torch's current stream (nlf/__init__.py:486-502); no hidden synchronisation except in
+ *     hr_render_host, which is synchronous by contract;
+ *   - a handle is re-entrant per handle, no global state except the thread-local error string;
+ *   - there is NO CPU fallback: if no sm_100 device is present hr_create fails.
+ */
+#ifndef HYPERREEL_B200_H
+#define HYPERREEL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HR_ABI_VERSION 3
+
+#define HR_MAX_GROUPS 4   /* ray-parameterisation groups feeding the sample net (ray.py:235-263) */
+#define HR_MAX_LAYERS 10  /* Linear layers of the sample net (mlp.py:127-154) */
+#define HR_MAX_SAMPLES 64 /* z_channels S (per-ray sample primitives) */
+
+/* Activation y = f(x*inner_fac + shift) * outer_fac  (nlf/activations.py:53-69,121-137,163-178).
+ * EaseValue (activations.py:462-496) is resolved on the host at render iteration to its inner act. */
+enum { HR_ACT_IDENTITY = 0, HR_ACT_SIGMOID = 1, HR_ACT_TANH = 2 };
+typedef struct hr_act {
+  int32_t kind;
+  float inner_fac, shift, outer_fac;
+} hr_act;
+
+/* One `params:` group of RayPredictionEmbedding (nlf/embedding/ray.py:235-263,320-326):
+ * rays[:, start:end] -> RayParam fn -> WindowedPE (all windows open). */
+enum { HR_PARAM_IDENTITY = 0, HR_PARAM_TWO_PLANE = 1, HR_PARAM_PLUECKER = 2 };
+typedef struct hr_encode_group {
+  int32_t start, end;        /* channel slice of the ray                                    */
+  int32_t fn;                /* HR_PARAM_* (nlf/param.py:20-24, 63-118, 223-256)             */
+  int32_t n_freqs;           /* WindowedPE bands 2^1..2^n (nlf/pe.py:148,210-221)            */
+  int32_t exclude_identity;  /* pe.py:160-168                                               */
+  float freq_mult;           /* freq_multiplier (pe.py:147)                                 */
+  float base_mult;           /* base_multiplier (pe.py:151)                                 */
+  float near, far;           /* two_plane plane offsets (param.py:78-79)                    */
+  float dir_mult, mom_mult;  /* pluecker multipliers (param.py:236-237)                     */
+} hr_encode_group;
+
+enum { HR_ISECT_Z_PLANE = 0, HR_ISECT_SPHERE = 1 };
+enum { HR_CONTRACT_NONE = 0, HR_CONTRACT_MIPNERF = 1 };
+enum { HR_SHADE_SH = 0, HR_SHADE_RGB = 1 };
+enum { HR_DENSE_RELU = 0, HR_DENSE_SOFTPLUS = 1, HR_DENSE_RELU_ABS = 2 };
+
+/* Sample-net arithmetic.  FP32_SIMT: fp32 FMA on CUDA cores (bit-level closest to the reference's
+ * cuBLAS SGEMM).  BF16X3_TC: tcgen05 tensor cores, every fp32 operand split into bf16 hi+lo and the
+ * three leading cross products accumulated in fp32 TMEM (error ~2^-16 per product). */
+enum { HR_MLP_FP32_SIMT = 0, HR_MLP_BF16X3_TC = 1 };
+
+/* The recognised pipeline signature; one struct describes what the
+ * reference assembles from conf/experiment/model/<name>.yaml.  Anything the YAML asks for that this
+ * struct cannot express is rejected by the host binding at construction (no fallback). */
+typedef struct hr_config {
+  int32_t abi_version;  /* = HR_ABI_VERSION */
+  int32_t c_in;         /* ray channels: 6 static, 8 video (datasets/technicolor.py:360-396) */
+
+  /* --- sample-prediction net input (a5,a6) --- */
+  int32_t n_groups;
+  hr_encode_group groups[HR_MAX_GROUPS];
+
+  /* --- sample-prediction net (a7): nlf/nets/mlp.py:60-178 --- */
+  int32_t mlp_in;      /* sum of PE output channels                                   */
+  int32_t mlp_width;   /* hidden_channels W                                           */
+  int32_t mlp_layers;  /* number of Linear layers = yaml depth (ray.py:283-285)        */
+  int32_t mlp_skip;    /* index of the layer whose input is cat([in, h]) or -1         */
+  int32_t mlp_out;     /* S * head_stride                                             */
+  float leaky_slope;   /* 0.01 (activations.py:14-29)                                 */
+  int32_t mlp_mode;    /* HR_MLP_*                                                    */
+
+  /* --- per-sample heads (a8): ray.py:331-337; channel offsets inside one sample, -1 = absent --- */
+  int32_t n_samples;    /* S                                                          */
+  int32_t head_stride;  /* channels per sample (15 for the shipped targets)            */
+  int32_t off_z, n_z;   /* z_vals: 1 channel (z_plane) or 4 (sphere: origin3 + radius) */
+  int32_t off_flow, off_sigma, off_point_sigma, off_offset, off_cscale, off_cshift;
+  hr_act act_z, act_flow, act_sigma, act_point_sigma, act_offset, act_cscale, act_cshift;
+
+  /* --- intersection (a10-a13): nlf/intersect/base.py:142-259 --- */
+  int32_t isect_type;             /* HR_ISECT_*                                        */
+  hr_act isect_act;               /* `activation:` of the intersect block (base.py:119) */
+  int32_t isect_use_sigma;        /* base.py:155-161                                   */
+  int32_t isect_density_off;      /* head channel used as sigma there, -1 = zeros      */
+  float z_scale;                  /* |samples[1]-samples[0]| (z.py:60-71)              */
+  float isect_near, isect_far;    /* mask bounds (base.py:194-203)                     */
+  int32_t isect_sort;             /* base.py:206-210                                   */
+  float samples[HR_MAX_SAMPLES];  /* base primitives, host-computed linspace (z.py:50-57) */
+  int32_t contract_type;          /* HR_CONTRACT_* (nlf/contract.py:113-192)           */
+  int32_t contract_samples;       /* inverse-contract z before intersecting (base.py:132-133) */
+  float contract_start_radius, contract_end_radius;      /* end may be +inf          */
+  float contract_start_distance, contract_end_distance;
+  float sphere_origin_initial[3]; /* primitive.py:388                                  */
+  float sphere_origin_scale;      /* origin_scale_factor (primitive.py:387)            */
+
+  /* --- keyframe snap + flow (a14): nlf/embedding/point.py:780-831, utils/flow_utils.py:10-35 --- */
+  int32_t use_flow;
+  int32_t num_keyframes, num_frames;  /* K, F                                          */
+  hr_act flow_act;                    /* spatial_flow_activation (point.py:817)         */
+
+  /* --- point offset (a15): point.py:371-396 --- */
+  int32_t use_offset;
+  int32_t offset_density_off;  /* head channel of `in_density_field`, -1 = zeros       */
+  hr_act offset_act;
+
+  /* --- TensoRF decode + composite (a17-a23) --- */
+  int32_t dynamic;      /* 1: tensor_vm_split_time, 0: tensor_vm_split_no_sample         */
+  float aabb[6];        /* min xyz, max xyz (tensorf_base.py:148)                        */
+  float distance_scale; /* tensorf_base.py:212                                          */
+  int32_t n_sigma[3];   /* n_lamb_sigma                                                 */
+  int32_t n_app[3];     /* n_lamb_sh                                                    */
+  int32_t app_dim;      /* data_dim_color: 27 (SH) or 3 (RGB)                           */
+  int32_t shading;      /* HR_SHADE_*                                                   */
+  int32_t white_bg, black_bg;
+  float weight_thre;    /* rm_weight_mask_thre                                          */
+  int32_t fea2dense;    /* HR_DENSE_*                                                   */
+  float density_shift;
+  int32_t use_color_scale_shift; /* 'color_scale' reaches the colour net (tensorf_dynamic.py:780-784) */
+  int32_t clamp_output; /* eval(): clamp(0,1) (tensorf_dynamic.py:805-806)              */
+} hr_config;
+
+/* Parameters in the reference's own state_dict layout, fp32, contiguous.
+ * hr_upload re-lays them out on the device (channel-last tables, packed / split net weights) into
+ * memory owned by the handle; the caller's buffers are not referenced after the call returns
+ * (device sources: after the stream reaches that point). */
+typedef struct hr_params {
+  int32_t on_device;                     /* 1: pointers are device pointers, 0: host     */
+  const float* mlp_weight[HR_MAX_LAYERS];/* layers.{l}[.0].weight  [out_l, in_l] row-major */
+  const float* mlp_bias[HR_MAX_LAYERS];  /* layers.{l}[.0].bias    [out_l]               */
+  /* density_plane[_space].{i} / app_plane[_space].{i}: [1, C_i, H_i, W_i]  (C_i may be 0 -> NULL) */
+  const float* sigma_plane[3];
+  const float* app_plane[3];
+  int32_t plane_h[3], plane_w[3];
+  /* second factor: dynamic  density_plane_time.{i} / app_plane_time.{i}  [1, C_i, K, L_i]
+   *                static   density_line.{i}       / app_line.{i}        [1, C_i, L_i, 1]      */
+  const float* sigma_second[3];
+  const float* app_second[3];
+  int32_t second_len[3];                 /* L_i                                          */
+  const float* basis_mat;                /* basis_mat.weight [app_dim, sum(n_app)]       */
+} hr_params;
+
+typedef struct hr_handle hr_handle;
+
+/* Version of this ABI (compare with HR_ABI_VERSION). */
+int hr_abi_version(void);
+
+/* Last error message of the calling thread ("" if none).  Replaces: Python exceptions. */
+const char* hr_last_error(void);
+
+/* Replaces: model_dict['lightfield'](cfg.model, system) + render_fn_dict['lightfield'](...)
+ * construction (nlf/__init__.py:351-364, nlf/models/models.py:104-129, nlf/rendering.py:59-70).
+ * `device` is the CUDA ordinal.  Fails if the device is not sm_100 or the signature is unsupported. */
+int hr_create(const hr_config* cfg, int device, hr_handle** out);
+
+/* Replaces: INRSystem.load_state_dict (nlf/__init__.py:433-479) for the render path: ingest a
+ * state_dict (any grid size: sizes come from the tensors, Appendix B), pack for the kernels. */
+int hr_upload(hr_handle* h, const hr_params* p, void* stream);
+
+/* Bytes of scratch hr_render needs for n rays (per-ray sample-net outputs). */
+int64_t hr_workspace_bytes(const hr_handle* h, int64_t n_rays);
+
+/* Replaces: RenderLightfield.forward -> LightfieldModel.forward (nlf/rendering.py:72-77,
+ * nlf/models/models.py:135-138) for one chunk: rays [n, c_in] fp32 device -> rgb [n,3] fp32 device.
+ * `workspace` is device scratch of at least hr_workspace_bytes(h, n) bytes (16B aligned). */
+int hr_render(hr_handle* h, const float* rays, int64_t n_rays, float* rgb,
+              void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Debug/bisect variant (SURVEY.md section 4 "stage-boundary tests").  Any output pointer may be
+ * NULL.  mlp_out [n, mlp_out] is in the reference's order (sample-major, ray.py:333);
+ * distances [n,S] sorted t (base.py:206-210,257); points [n,S,3] final sample points (after flow
+ * and offset); sigma [n,S]; weights [n,S] compositing weights (tensorf_utils.py:242-253). */
+int hr_render_stages(hr_handle* h, const float* rays, int64_t n_rays, float* rgb,
+                     float* mlp_out, float* distances, float* points, float* sigma, float* weights,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Replaces: INRSystem.forward(coords) on HOST buffers, i.e. the `.cuda()` upload, render_chunked
+ * (nlf/rendering.py:100-150) and the `.cpu()` read-back of validation_video
+ * (nlf/__init__.py:828-855).  rays_host/rgb_host should be pinned; the call splits the batch in
+ * `chunk` rays (0 = default), overlaps H2D / kernels / D2H on internal streams and returns when the
+ * rgb is on the host. */
+int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* rgb_host, int64_t chunk);
+
+/* Number of kernels hr_render launched since creation (bench.py's gpu_launches). */
+int64_t hr_launch_count(const hr_handle* h);
+
+/* Average device time (ms, CUDA events on the launching stream) of the dominant kernel -- the fused
+ * gather+decode+composite kernel -- over launches since the last hr_timing_reset; needs
+ * hr_timing_enable(h, 1).  Used by bench.py for roofline.achieved. */
+int hr_timing_enable(hr_handle* h, int enable);
+int hr_timing_reset(hr_handle* h);
+int hr_timing_read(hr_handle* h, double* render_ms_avg, double* mlp_ms_avg, int64_t* launches);
+
+/* Replaces: module destruction. */
+int hr_destroy(hr_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPERREEL_B200_H */

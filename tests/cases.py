@@ -1,0 +1,60 @@
+"""Seeded parity cases shared by the golden generator, the oracle tests and the GPU parity tests.
+
+Every case is (built-in model config in the reference schema, dataset facts, overrides, ray count, parameter
+seed, density gain).  ``density_gain`` > 1 gives the "trained-like" variant in which transmittance saturates
+along the ray, so all samples -- not only the last one -- contribute to the pixel.
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass
+from typing import Dict
+
+import torch
+
+from hyperreel_b200 import configs, rays as rays_mod
+from hyperreel_b200.config import to_plain
+from hyperreel_b200.signature import Signature, lower
+from hyperreel_b200.state import seeded_state_dict
+
+CASES: Dict[str, dict] = {
+    # name: builtin, overrides, rays, parameter seed, density gain
+    "technicolor_trained": dict(builtin="technicolor_z_plane", over=dict(n_voxels=48 ** 3), n=256, seed=0, gain=30.0),
+    "technicolor_init": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3), n=128, seed=3, gain=1.0),
+    "technicolor_k50": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, num_keyframes=50), n=128, seed=4, gain=30.0),
+    "neural3d_trained": dict(builtin="neural_3d_z_plane", over=dict(n_voxels=40 ** 3), n=160, seed=1, gain=30.0),
+    "donerf_trained": dict(builtin="donerf_sphere", over=dict(n_voxels=40 ** 3), n=256, seed=2, gain=30.0),
+    "donerf_s16": dict(builtin="donerf_sphere", over=dict(n_voxels=32 ** 3, z_channels=16), n=128, seed=5, gain=30.0),
+    "plumbing_4096x4": dict(builtin="donerf_sphere", over=dict(n_voxels=64 ** 3, z_channels=4), n=4096, seed=6, gain=30.0),
+    "shiny_tiny": dict(builtin="shiny_z_plane_tiny", over=dict(n_voxels=32 ** 3), n=256, seed=7, gain=30.0),
+}
+
+
+@dataclass
+class Case:
+    name: str
+    model_cfg: object
+    model_cfg_plain: dict
+    dataset: dict
+    sig: Signature
+    rays: torch.Tensor
+    state_dict: Dict[str, torch.Tensor]
+    n_samples: int
+
+
+def state_hash(sd: Dict[str, torch.Tensor]) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd.keys()):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def build_case(name: str, n: int = None) -> Case:
+    spec = CASES[name]
+    cfg, ds = configs.get(spec["builtin"], **spec["over"])
+    sig = lower(cfg, ds)
+    sd = seeded_state_dict(sig, seed=spec["seed"], density_gain=spec["gain"])
+    r = rays_mod.for_signature(sig, n or spec["n"], seed=100 + spec["seed"])
+    return Case(name=name, model_cfg=cfg, model_cfg_plain=to_plain(cfg), dataset=ds, sig=sig, rays=r, state_dict=sd,
+                n_samples=sig.n_samples)
