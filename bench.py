@@ -167,13 +167,13 @@ def run_ours(args):
             dist.all_gather_into_tensor(tiles.view(world * n, 3), rgb)  # the single collective: finished pixel tiles
         return rgb
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     model.timing(True)
     launches0 = model.launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

@@ -20,15 +20,26 @@ struct MlpSimtPack {
   int skip;
 };
 
-// tcgen05 path (HR_MLP_BF16X3_TC): see hr_mlp_tc.cu for the layout.
+// tcgen05 path (HR_MLP_BF16X3_TC): see hr_mlp_tc.cu.  A "pass" is one accumulator's worth of output columns
+// (a hidden layer, or <=256 columns of the last layer); its weights are stored as n_chunks*2 k-step images.
+#define HR_TC_MAX_PASSES 16
+struct TcPass {
+  int layer;        // Linear layer index
+  int n;            // output columns of this pass (multiple of 16, <= 256)
+  int first_chunk;  // first A chunk consumed (0 = encoded input, 1.. = hidden)
+  int n_chunks;     // chunks of 32 k
+  int bias_off;     // offset into the bias table
+  int is_final;     // last layer: results go to HBM instead of the next A operand
+  int out_col0;     // first output column (channel-major order) of a last-layer pass
+  int wait_a;       // the issuer must wait for the A chunks (first pass of a layer)
+};
 struct MlpTcPack {
-  const void* wpack;        // bf16 hi/lo weight tiles, UMMA canonical layout
-  const float* bias[HR_MAX_LAYERS];
-  long long layer_off[HR_MAX_LAYERS];  // byte offset of each layer's tiles in wpack
-  int n_layers;
-  int skip;
-  int in_pad;
-  int n_out_pad;
+  const void* wpack;   // bf16 hi/lo weight images, UMMA K-major no-swizzle layout, consumption order
+  const float* bias;   // [bias_count]
+  long long wpack_bytes;
+  int n_passes;
+  int bias_count;
+  TcPass passes[HR_TC_MAX_PASSES];
 };
 
 size_t mlp_simt_smem_bytes(const MlpSimtPack& pk, int W);

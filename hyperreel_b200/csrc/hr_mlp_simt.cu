@@ -8,6 +8,7 @@
 // the reference's SGEMM; this is the parity anchor for the tensor-core path.
 #include "hr_common.cuh"
 #include "hr_mlp.cuh"
+#include "hr_encode.cuh"
 
 namespace hr {
 
@@ -24,59 +25,6 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// RayPredictionEmbedding input encoding for one ray (nlf/embedding/ray.py:320-326).
-// Writes cfg.mlp_in values with stride `stride` starting at dst.
-__device__ void encode_ray(const hr_config& cfg, const float* __restrict__ ray, float* dst, int stride) {
-  int k = 0;
-  for (int g = 0; g < cfg.n_groups; ++g) {
-    const hr_encode_group& G = cfg.groups[g];
-    float v[8];
-    int dims;
-    const float* r = ray + G.start;
-    if (G.fn == HR_PARAM_TWO_PLANE) {
-      // TwoPlaneParam (param.py:87-115) + intersect_axis_plane (intersect_utils.py:127-150)
-      float oz = r[2], dz = r[5];
-      float dzg = (fabsf(dz) < 1e-5f) ? 1e12f : dz;
-      float t1 = __fdiv_rn(__fsub_rn(G.near, oz), dzg);
-      float t2 = __fdiv_rn(__fsub_rn(G.far, oz), dzg);
-      v[0] = __fadd_rn(r[0], __fmul_rn(r[3], t1));
-      v[1] = __fadd_rn(r[1], __fmul_rn(r[4], t1));
-      v[2] = __fadd_rn(r[0], __fmul_rn(r[3], t2));
-      v[3] = __fadd_rn(r[1], __fmul_rn(r[4], t2));
-      dims = 4;
-    } else if (G.fn == HR_PARAM_PLUECKER) {
-      // PlueckerParam (param.py:244-253)
-      float ox = r[0], oy = r[1], oz = r[2];
-      float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r[3], r[3]), __fmul_rn(r[4], r[4])), __fmul_rn(r[5], r[5])));
-      nrm = fmaxf(nrm, 1e-12f);
-      float dx = __fdiv_rn(r[3], nrm), dy = __fdiv_rn(r[4], nrm), dz = __fdiv_rn(r[5], nrm);
-      float mx = __fsub_rn(__fmul_rn(oy, dz), __fmul_rn(oz, dy));
-      float my = __fsub_rn(__fmul_rn(oz, dx), __fmul_rn(ox, dz));
-      float mz = __fsub_rn(__fmul_rn(ox, dy), __fmul_rn(oy, dx));
-      v[0] = __fmul_rn(dx, G.dir_mult);
-      v[1] = __fmul_rn(dy, G.dir_mult);
-      v[2] = __fmul_rn(dz, G.dir_mult);
-      v[3] = __fmul_rn(mx, G.mom_mult);
-      v[4] = __fmul_rn(my, G.mom_mult);
-      v[5] = __fmul_rn(mz, G.mom_mult);
-      dims = 6;
-    } else {
-      dims = G.end - G.start;
-      for (int i = 0; i < dims; ++i) v[i] = r[i];
-    }
-    // WindowedPE with all windows open (pe.py:210-221): [x | sin(f1 x) | cos(f1 x) | sin(f2 x) | ...]
-    if (!G.exclude_identity)
-      for (int i = 0; i < dims; ++i) dst[(k++) * stride] = v[i];
-    float freq = 1.0f;
-    for (int f = 0; f < G.n_freqs; ++f) {
-      freq = __fmul_rn(freq, G.freq_mult);  // freq_multiplier ** (f+1), exact for 2.0
-      float bf = __fmul_rn(G.base_mult, freq);
-      for (int i = 0; i < dims; ++i) dst[(k++) * stride] = sinf(__fmul_rn(bf, v[i]));
-      for (int i = 0; i < dims; ++i) dst[(k++) * stride] = cosf(__fmul_rn(bf, v[i]));
-    }
-  }
-}
 
 template <int W>
 __global__ void __launch_bounds__(NTHREADS, 1)

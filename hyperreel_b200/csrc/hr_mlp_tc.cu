@@ -1,14 +1,453 @@
-// Sample-prediction network on tcgen05 tensor cores (HR_MLP_BF16X3_TC) -- under construction.
+// Sample-prediction network on the 5th-generation tensor cores (HR_MLP_BF16X3_TC).
+//
+// Same math as hr_mlp_simt.cu (reference: nlf/nets/mlp.py:159-172 behind nlf/embedding/ray.py:320-326), but
+// every fp32 operand x is split into bf16 hi = rn(x) and lo = rn(x - hi) and each Linear layer is
+//   D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo          (fp32 accumulation in TMEM)
+// i.e. three tcgen05.mma (kind::f16, bf16 inputs) per k-step; the dropped A_lo*B_lo term and the split
+// residuals are O(2^-16) relative per product (DESIGN.md "precision of the tensor-core sample net").
+//
+// One persistent CTA per SM, one 128-ray tile at a time (UMMA M = 128, one TMEM lane per ray):
+//   warps 0-3  epilogue: thread = ray.  Encode the ray, then per layer read the accumulator from TMEM
+//              (tcgen05.ld 32x32b), add bias, LeakyReLU, split to bf16 hi/lo and write the next layer's A
+//              operand straight into shared memory in the UMMA K-major no-swizzle ("interleave") layout;
+//              for the last layer transpose through shared memory and store coalesced rows to HBM.
+//   warp 4     producer: streams the pre-packed weight images (one 16-wide k-step of one pass: bf16 hi and lo,
+//              already in UMMA layout) through a 4-stage ring with cp.async.bulk + mbarrier complete_tx.
+//   warp 5     MMA issuer: one lane issues tcgen05.mma / tcgen05.commit, trailing the epilogue chunk by chunk
+//              (a_ready barriers per 32-column chunk), with two 256-column TMEM accumulators ping-ponged
+//              across layers so layer l+1's MMAs overlap layer l's epilogue.
+#include <cuda_bf16.h>
+
+#include <cstring>
+
+#include "hr_encode.cuh"
 #include "hr_handle.h"
 
 namespace hr {
 
-int pack_mlp_tc(hr_handle*, const hr_params*, const float* const*, const float* const*, cudaStream_t) {
-  return hr_fail("HR_MLP_BF16X3_TC: tensor-core sample net not built into this library yet");
+namespace tc {
+
+constexpr int BM = 128;            // rays per tile (UMMA M)
+constexpr int NSTAGE = 4;          // weight ring depth
+constexpr int STAGE_BYTES = 16384; // one k-step image: N<=256 rows x 16 k x (hi+lo) bf16
+constexpr int CHUNK_BYTES = 8192;  // one A chunk: 128 rows x 32 k bf16
+constexpr int NCHUNK = 9;          // chunk 0 = encoded input (32, zero padded), chunks 1..8 = hidden 256
+constexpr int NTHREADS = 192;
+constexpr int BIAS_FLOATS = 2560;
+
+// shared memory map (bytes)
+constexpr int OFF_A_HI = 0;
+constexpr int OFF_A_LO = OFF_A_HI + NCHUNK * CHUNK_BYTES;   // 73728
+constexpr int OFF_B = OFF_A_LO + NCHUNK * CHUNK_BYTES;      // 147456
+constexpr int OFF_BIAS = OFF_B + NSTAGE * STAGE_BYTES;      // 212992
+constexpr int OFF_BAR = OFF_BIAS + BIAS_FLOATS * 4;         // 223232
+constexpr int SMEM_BYTES = OFF_BAR + 256;                   // 223488
+
+// barrier slots (8 bytes each) inside OFF_BAR
+constexpr int BAR_FULL = 0;                 // [NSTAGE]
+constexpr int BAR_EMPTY = BAR_FULL + NSTAGE;   // [NSTAGE]
+constexpr int BAR_AREADY = BAR_EMPTY + NSTAGE; // [NCHUNK]
+constexpr int BAR_DFULL = BAR_AREADY + NCHUNK; // [2]
+constexpr int BAR_DEMPTY = BAR_DFULL + 2;      // [2]
+constexpr int BAR_TMEMPTR = BAR_DEMPTY + 2;    // 4-byte TMEM base address lives in this slot
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, no-swizzle UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start>>4 | [16,30) leading (K-direction core-matrix) byte offset>>4 | [32,46) stride (M/N-direction) byte
+//   offset>>4 | [46,48) version = 1 | [61,64) layout type = 0 (SWIZZLE_NONE)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// Instruction descriptor (InstrDescriptor): c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B,
+// n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-cudaError_t launch_mlp_tc(const hr_config&, const MlpTcPack&, const float*, float*, long long, int, cudaStream_t) {
-  return cudaErrorNotSupported;
+// Offset (bytes) of the 16-byte row slot holding k-group kg of row `row` inside a 128-row x 32-k chunk.
+__device__ __forceinline__ uint32_t a_slot(int row, int kg) { return (uint32_t)((kg * 16 + (row >> 3)) * 128 + (row & 7) * 16); }
+
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    float r0 = x[2 * i] - __low2float(hh);
+    float r1 = x[2 * i + 1] - __high2float(hh);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+}  // namespace tc
+
+__global__ void __launch_bounds__(tc::NTHREADS, 1)
+mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ MlpTcPack pk, const float* __restrict__ rays,
+              float* __restrict__ heads, long long n_rays) {
+  using namespace tc;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+  auto bar = [&](int slot) -> uint32_t { return sbase + OFF_BAR + slot * 8; };
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + BAR_TMEMPTR * 8);
+
+  // ---- one-time setup ----
+  for (int i = tid; i < pk.bias_count; i += NTHREADS) s_bias[i] = pk.bias[i];
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(BAR_FULL + s), 1); mbar_init(bar(BAR_EMPTY + s), 1); }
+    for (int c = 0; c < NCHUNK; ++c) mbar_init(bar(BAR_AREADY + c), 128);
+    for (int d = 0; d < 2; ++d) { mbar_init(bar(BAR_DFULL + d), 1); mbar_init(bar(BAR_DEMPTY + d), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    uint32_t dst = sbase + OFF_BAR + BAR_TMEMPTR * 8;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(dst) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const long long n_tiles = (n_rays + BM - 1) / BM;
+  const int n_passes = pk.n_passes;
+
+  if (warp == 4) {
+    // =========================== producer: weight images, in consumption order ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(pk.wpack);
+        for (int p = 0; p < n_passes; ++p) {
+          const uint32_t bytes = (uint32_t)pk.passes[p].n * 64u;
+          const int n_img = pk.passes[p].n_chunks * 2;
+          for (int i = 0; i < n_img; ++i, ++it) {
+            const uint32_t s = it % NSTAGE;
+            mbar_wait(bar(BAR_EMPTY + s), ((it / NSTAGE) & 1) ^ 1);
+            mbar_expect_tx(bar(BAR_FULL + s), bytes);
+            bulk_g2s(sbase + OFF_B + s * STAGE_BYTES, src, bytes, bar(BAR_FULL + s));
+            src += bytes;
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      uint32_t it = 0, gp = 0, titer = 0;
+      const int n_hidden = cfg.mlp_layers - 1;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+        for (int p = 0; p < n_passes; ++p, ++gp) {
+          const TcPass& P = pk.passes[p];
+          const uint32_t db = gp & 1, use = gp >> 1;
+          const uint32_t d_tmem = tmem_base + db * 256;
+          const uint32_t idesc = umma_idesc(P.n);
+          mbar_wait(bar(BAR_DEMPTY + db), (use & 1) ^ 1);  // accumulator drained by its previous reader
+          for (int ci = 0; ci < P.n_chunks; ++ci) {
+            const int c = P.first_chunk + ci;
+            if (P.wait_a) {
+              // chunk 0: written once per tile by the encoder; chunks 1..8: once per hidden layer
+              const uint32_t done = (c == 0) ? titer : (titer * n_hidden + (uint32_t)(P.layer - 1));
+              mbar_wait(bar(BAR_AREADY + c), done & 1);
+            }
+            for (int ks = 0; ks < 2; ++ks, ++it) {
+              const uint32_t s = it % NSTAGE;
+              mbar_wait(bar(BAR_FULL + s), (it / NSTAGE) & 1);
+              tc_fence_after();
+              const uint32_t a_off = c * CHUNK_BYTES + ks * 4096;
+              const uint64_t a_hi = umma_desc(sbase + OFF_A_HI + a_off, 2048, 128);
+              const uint64_t a_lo = umma_desc(sbase + OFF_A_LO + a_off, 2048, 128);
+              const uint32_t b_addr = sbase + OFF_B + s * STAGE_BYTES;
+              const uint64_t b_hi = umma_desc(b_addr, (uint32_t)P.n * 16, 128);
+              const uint64_t b_lo = umma_desc(b_addr + (uint32_t)P.n * 32, (uint32_t)P.n * 16, 128);
+              const uint32_t first = (ci == 0 && ks == 0) ? 0u : 1u;
+              umma_bf16(d_tmem, a_hi, b_hi, idesc, first);
+              umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_commit(bar(BAR_EMPTY + s));  // frees the weight stage when these MMAs retire
+            }
+          }
+          umma_commit(bar(BAR_DFULL + db));  // accumulator complete -> epilogue
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue warps: thread = ray ===========================
+    const int row = tid;  // 0..127, TMEM lane
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    uint32_t gp = 0;
+    // transpose staging: the chunk-0 slots of A_hi (warps 0,1) and A_lo (warps 2,3), 4 KB per warp; chunk 0 is only
+    // read by the first and the skip layer's MMAs, which have retired before any last-layer accumulator is full
+    float* stage_f = reinterpret_cast<float*>(smem + ((warp < 2) ? OFF_A_HI : OFF_A_LO)) + (warp & 1) * 1024;
+    bool first_tile = true;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long ray = tile * BM + row;
+      // all four warps must be done reading the staging area (previous tile) before chunk 0 is rewritten
+      if (!first_tile) asm volatile("bar.sync 1, 128;" ::: "memory");
+      first_tile = false;
+      // ---- encode (RayParam + WindowedPE), split, write chunk 0 ----
+      {
+        float enc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) enc[i] = 0.0f;
+        if (ray < n_rays) encode_ray(cfg, rays + ray * cfg.c_in, enc, 1);
+#pragma unroll
+        for (int kg = 0; kg < 4; ++kg) {
+          uint4 hi, lo;
+          split8(enc + kg * 8, hi, lo);
+          *reinterpret_cast<uint4*>(smem + OFF_A_HI + a_slot(row, kg)) = hi;
+          *reinterpret_cast<uint4*>(smem + OFF_A_LO + a_slot(row, kg)) = lo;
+        }
+        fence_async_smem();
+        mbar_arrive(bar(BAR_AREADY + 0));
+      }
+      for (int p = 0; p < n_passes; ++p, ++gp) {
+        const TcPass& P = pk.passes[p];
+        const uint32_t db = gp & 1, use = gp >> 1;
+        mbar_wait(bar(BAR_DFULL + db), use & 1);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + lane_base + db * 256;
+        const float* bias = s_bias + P.bias_off;
+        if (!P.is_final) {
+          for (int j = 0; j < 8; ++j) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + j * 32, v);
+            if (j == 7) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg) {
+              float x[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float t = __uint_as_float(v[kg * 8 + i]) + bias[j * 32 + kg * 8 + i];
+                x[i] = (t > 0.0f) ? t : t * cfg.leaky_slope;
+              }
+              uint4 hi, lo;
+              split8(x, hi, lo);
+              const uint32_t off = (1 + j) * CHUNK_BYTES + a_slot(row, kg);
+              *reinterpret_cast<uint4*>(smem + OFF_A_HI + off) = hi;
+              *reinterpret_cast<uint4*>(smem + OFF_A_LO + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(bar(BAR_AREADY + 1 + j));
+          }
+        } else {
+          const int nchunks = (P.n + 31) / 32;
+          for (int j = 0; j < nchunks; ++j) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + j * 32, v);
+            if (j == nchunks - 1) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+            // transpose through shared memory (XOR swizzle, conflict free) -> coalesced row stores
+#pragma unroll
+            for (int i = 0; i < 32; ++i) stage_f[lane * 32 + (i ^ lane)] = __uint_as_float(v[i]) + bias[j * 32 + i];
+            __syncwarp();
+            const int col = P.out_col0 + j * 32 + lane;
+            const bool col_ok = (j * 32 + lane < P.n) && (col < cfg.mlp_out);
+            for (int rr = 0; rr < 32; ++rr) {
+              const long long r = tile * BM + warp * 32 + rr;
+              float o = stage_f[rr * 32 + (lane ^ rr)];
+              if (col_ok && r < n_rays) heads[r * cfg.mlp_out + col] = o;
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// weight packing: fp32 reference weights -> bf16 hi/lo images in UMMA K-major no-swizzle layout, consumption order
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void pack_tc_pass(const float* __restrict__ W, const float* __restrict__ b, uint8_t* __restrict__ dst,
+                             float* __restrict__ bias_dst, int n, int first_chunk, int n_chunks, int in_src, int mlp_in,
+                             int is_skip, int is_first, int out_rows, int perm_S, int perm_stride, int out_col0) {
+  // one thread per (image, n, kk)
+  const long long total = (long long)n_chunks * 2 * n * 16;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total + n; i += (long long)gridDim.x * blockDim.x) {
+    if (i >= total) {
+      int nn = (int)(i - total);
+      int ncol = out_col0 + nn;  // output column (channel-major for the last layer)
+      float v = 0.0f;
+      if (ncol < out_rows) {
+        int ns = perm_S > 0 ? (ncol % perm_S) * perm_stride + (ncol / perm_S) : ncol;
+        v = b[ns];
+      }
+      bias_dst[nn] = v;
+      continue;
+    }
+    int kk = (int)(i % 16);
+    int nn = (int)((i / 16) % n);
+    int img = (int)(i / (16LL * n));
+    int c = first_chunk + img / 2, ks = img % 2;
+    int kc = ks * 16 + kk;  // k inside the chunk
+    // source column of the reference weight
+    int ksrc = -1;
+    if (c == 0) {
+      if (kc < mlp_in) ksrc = kc;  // encoded input (first layer, or the input part of the skip layer)
+    } else {
+      int hcol = (c - 1) * 32 + kc;
+      ksrc = is_skip ? mlp_in + hcol : hcol;
+    }
+    (void)is_first;
+    int ncol = out_col0 + nn;
+    float w = 0.0f;
+    if (ncol < out_rows && ksrc >= 0 && ksrc < in_src) {
+      int ns = perm_S > 0 ? (ncol % perm_S) * perm_stride + (ncol / perm_S) : ncol;
+      w = W[(long long)ns * in_src + ksrc];
+    }
+    __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    size_t img_off = (size_t)img * n * 64;
+    size_t slot = (size_t)(((kk >> 3) * (n >> 3) + (nn >> 3)) * 128 + (nn & 7) * 16 + (kk & 7) * 2);
+    *reinterpret_cast<__nv_bfloat16*>(dst + img_off + slot) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(dst + img_off + (size_t)n * 32 + slot) = lo;
+  }
+}
+
+int pack_mlp_tc(hr_handle* h, const hr_params*, const float* const* w_dev, const float* const* b_dev, cudaStream_t st) {
+  const hr_config& c = h->cfg;
+  MlpTcPack& pk = h->tc;
+  memset(&pk, 0, sizeof(pk));
+  if (c.mlp_width != 256) return hr_fail("tensor-core sample net: width must be 256");
+  if (c.mlp_in > 32) return hr_fail("tensor-core sample net: encoded input wider than 32");
+  const int L = c.mlp_layers;
+  int np = 0, bias_off = 0;
+  size_t bytes = 0;
+  for (int l = 0; l < L; ++l) {
+    const bool last = (l == L - 1);
+    const int n_parts = last ? (c.mlp_out + 255) / 256 : 1;
+    const int n_each = last ? (((c.mlp_out + n_parts - 1) / n_parts + 15) / 16 * 16) : 256;
+    for (int part = 0; part < n_parts; ++part) {
+      if (np >= HR_TC_MAX_PASSES) return hr_fail("tensor-core sample net: too many passes");
+      TcPass& P = pk.passes[np++];
+      P.layer = l;
+      P.n = n_each;
+      P.first_chunk = (l == 0 || l == c.mlp_skip) ? 0 : 1;
+      P.n_chunks = (l == 0) ? 1 : (l == c.mlp_skip ? 9 : 8);
+      P.bias_off = bias_off;
+      P.is_final = last ? 1 : 0;
+      P.out_col0 = part * n_each;
+      P.wait_a = (part == 0) ? 1 : 0;
+      bias_off += n_each;
+      bytes += (size_t)P.n_chunks * 2 * P.n * 64;
+    }
+  }
+  if (bias_off > tc::BIAS_FLOATS) return hr_fail("tensor-core sample net: bias table too large");
+  pk.n_passes = np;
+  pk.bias_count = bias_off;
+  uint8_t* wp = nullptr;
+  float* bp = nullptr;
+  cudaError_t e = cudaMalloc((void**)&wp, bytes);
+  if (e != cudaSuccess) return hr_fail("cudaMalloc(tc weights %zu): %s", bytes, cudaGetErrorString(e));
+  h->owned.push_back(wp);
+  e = cudaMalloc((void**)&bp, (size_t)bias_off * sizeof(float));
+  if (e != cudaSuccess) return hr_fail("cudaMalloc(tc bias): %s", cudaGetErrorString(e));
+  h->owned.push_back(bp);
+  size_t off = 0;
+  for (int p = 0; p < np; ++p) {
+    const TcPass& P = pk.passes[p];
+    const int l = P.layer;
+    const bool last = (l == L - 1), skip = (l == c.mlp_skip), first = (l == 0);
+    const int in_src = first ? c.mlp_in : (skip ? c.mlp_in + 256 : 256);
+    const int out_rows = last ? c.mlp_out : 256;
+    long long total = (long long)P.n_chunks * 2 * P.n * 16 + P.n;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    pack_tc_pass<<<grid, 256, 0, st>>>(w_dev[l], b_dev[l], wp + off, bp + P.bias_off, P.n, P.first_chunk, P.n_chunks, in_src,
+                                       c.mlp_in, skip ? 1 : 0, first ? 1 : 0, out_rows, last ? c.n_samples : 0,
+                                       c.head_stride, P.out_col0);
+    off += (size_t)P.n_chunks * 2 * P.n * 64;
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return hr_fail("tc pack launch failed: %s", cudaGetErrorString(e));
+  pk.wpack = wp;
+  pk.bias = bp;
+  pk.wpack_bytes = (long long)bytes;
+  return 0;
+}
+
+cudaError_t launch_mlp_tc(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
+                          int num_sms, cudaStream_t stream) {
+  long long tiles = (n + tc::BM - 1) / tc::BM;
+  int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  if (grid < 1) grid = 1;
+  cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  mlp_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, stream>>>(cfg, pk, rays, heads, n);
+  return cudaGetLastError();
 }
 
 }  // namespace hr
