@@ -300,6 +300,18 @@ int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
     if ((rc = pack_tab(p->app_second[i], C, H2, ts.L, &ta.second))) break;
   }
   if (!rc) {
+    // every table derives from one gridSize (tensorf_base.py:911-944, tensorf_dynamic.py:126-169): plane i is
+    // [C, grid[b_i], grid[a_i]], its second factor runs along grid[v_i]
+    const int rx = p->plane_w[0], ry = p->plane_h[0], rz = p->second_len[0];
+    h->dv.res[0] = rx; h->dv.res[1] = ry; h->dv.res[2] = rz;
+    h->dv.kt = c.dynamic ? c.num_keyframes : 1;
+    if (c.dynamic && c.num_keyframes < 2) rc = fail("hr_upload: the keyframe (time) planes need at least 2 keyframes");
+    if (c.n_sigma[1] > 0 && (p->plane_w[1] != rx || p->plane_h[1] != rz || p->second_len[1] != ry))
+      rc = fail("hr_upload: table group 1 is inconsistent with grid %dx%dx%d", rx, ry, rz);
+    if (!rc && c.n_sigma[2] > 0 && (p->plane_w[2] != ry || p->plane_h[2] != rz || p->second_len[2] != rx))
+      rc = fail("hr_upload: table group 2 is inconsistent with grid %dx%dx%d", rx, ry, rz);
+  }
+  if (!rc) {
     if (!p->basis_mat) rc = fail("hr_upload: basis_mat missing");
     else {
       const float* d = nullptr;

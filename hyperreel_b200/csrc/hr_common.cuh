@@ -37,6 +37,8 @@ struct Derived {
   float dist_scale_fac; // 1/(1-inv_end_dist)
   float inv_end_rad;    // contract_start_radius / contract_end_radius (contract.py:184)
   float rad_scale_fac;  // 1/(1-inv_end_rad)
+  int res[3];           // grid resolution along x, y, z (taken from the uploaded tables)
+  int kt;               // rows of the (axis, time) planes = number of keyframes
 };
 
 // Optional per-sample dumps for stage-boundary parity tests (all may be null).

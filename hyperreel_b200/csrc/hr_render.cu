@@ -16,78 +16,10 @@
 namespace hr {
 
 static constexpr int kWarpsPerCta = 8;
+static constexpr int kMinCtasPerSm = 3;
 static constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-template <int C>
-struct TapSet {
-  float4 a, b;
-  float w0, w1;
-};
-
-// Issue the loads of one bilinear footprint (reference: grid_sample, bilinear, zeros padding,
-// align_corners=True; unnormalise ((g+1)/2)*(size-1)).  gx indexes W, gy indexes H.
-// x0/y0 are clamped to [0, size-2] and the fraction recomputed, which is exact for in-range
-// coordinates (the out-of-range neighbour of a point on the max face has weight 0 in the reference).
-template <int C>
-__device__ __forceinline__ void issue(TapSet<C>& t, const float* __restrict__ tab, int H, int W, float gx, float gy,
-                                      int xt, int alt, bool pred) {
-  float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(W - 1));
-  int x0 = (int)floorf(ix);
-  x0 = max(0, min(x0, W - 2));
-  float fx = ix - (float)x0;
-  int y0 = 0, y1 = 0;
-  float fy = 0.0f;
-  if (H > 1) {
-    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(H - 1));
-    y0 = (int)floorf(iy);
-    y0 = max(0, min(y0, H - 2));
-    fy = iy - (float)y0;
-    y1 = y0 + 1;
-  }
-  float wx = xt ? fx : 1.0f - fx;
-  int x = min(x0 + xt, W - 1);
-  t.a = make_float4(0.f, 0.f, 0.f, 0.f);
-  t.b = make_float4(0.f, 0.f, 0.f, 0.f);
-  if constexpr (C == 8) {
-    t.w0 = wx * (1.0f - fy);
-    t.w1 = wx * fy;
-    if (pred) {
-      t.a = ldg4(tab + ((size_t)y0 * W + x) * 8 + alt * 4);
-      if (H > 1) t.b = ldg4(tab + ((size_t)y1 * W + x) * 8 + alt * 4);
-    }
-  } else {
-    int y = alt ? y1 : y0;
-    t.w0 = wx * (alt ? fy : 1.0f - fy);
-    t.w1 = 0.0f;
-    if (pred) t.a = ldg4(tab + ((size_t)y * W + x) * 4);
-  }
-}
-
-// Finish the interpolation across the quad.  C=8: out = this lane's 4-channel half (alt selects
-// channels 4*alt..4*alt+3).  C=4: out = all 4 channels, replicated on the 4 lanes.
-template <int C>
-__device__ __forceinline__ void combine(const TapSet<C>& t, float (&out)[4]) {
-  if constexpr (C == 8) {
-    out[0] = t.w0 * t.a.x + t.w1 * t.b.x;
-    out[1] = t.w0 * t.a.y + t.w1 * t.b.y;
-    out[2] = t.w0 * t.a.z + t.w1 * t.b.z;
-    out[3] = t.w0 * t.a.w + t.w1 * t.b.w;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] += __shfl_xor_sync(kFull, out[c], 2);
-  } else {
-    out[0] = t.w0 * t.a.x;
-    out[1] = t.w0 * t.a.y;
-    out[2] = t.w0 * t.a.z;
-    out[3] = t.w0 * t.a.w;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      out[c] += __shfl_xor_sync(kFull, out[c], 1);
-      out[c] += __shfl_xor_sync(kFull, out[c], 2);
-    }
-  }
-}
 
 // Ascending bitonic sort of 32*SPL keys, element e = reg*32 + lane (reference: torch.argsort +
 // gather of the distances only, utils/intersect_utils.py:12-16; ties are equal values).
@@ -162,87 +94,246 @@ __device__ __forceinline__ void sh_basis9(float x, float y, float z, float (&Y)[
   Y[8] = C24 * (xx - yy);
 }
 
-__host__ __device__ inline int basis_block_stride(int rows, int nt) {
-  int bs = rows * nt;
-  while ((bs & 31) != 8) ++bs;
-  return bs;
+// One factor table fetch for one sample, spread over the 4 lanes of a quad.
+//   C == 8 : lane (xt, alt) reads the 16-byte half `alt` of texel x0+xt in rows y0 (a) and y0+1 (b)
+//   C == 4 : lane (xt, yt=alt) reads the whole 16-byte texel (x0+xt, y0+yt) into a
+// `off` is the element offset of texel (x0, y0) * C already advanced to this lane's slice; `rs` the row stride in
+// elements.  Coordinates are clamped to [0, size-2] on the producer side, so every address is in range and the
+// loads need no predicate (invalid samples are redirected to offset 0 and zero-weighted).
+template <int C, bool ROWS2>
+struct Taps {
+  float4 a, b;
+};
+
+template <int C, bool ROWS2>
+__device__ __forceinline__ void fetch(Taps<C, ROWS2>& t, const float* __restrict__ tab, int off, int rs) {
+  t.a = ldg4(tab + off);
+  if constexpr (C == 8 && ROWS2) t.b = ldg4(tab + off + rs);
+}
+
+// Interpolate across the quad.  C == 8: result = this lane's 4-channel half; C == 4: all 4 channels (replicated).
+template <int C, bool ROWS2>
+__device__ __forceinline__ void interp(const Taps<C, ROWS2>& t, float w0, float w1, float (&out)[4]) {
+  if constexpr (C == 8) {
+    if constexpr (ROWS2) {
+      out[0] = fmaf(w1, t.b.x, w0 * t.a.x);
+      out[1] = fmaf(w1, t.b.y, w0 * t.a.y);
+      out[2] = fmaf(w1, t.b.z, w0 * t.a.z);
+      out[3] = fmaf(w1, t.b.w, w0 * t.a.w);
+    } else {
+      out[0] = w0 * t.a.x; out[1] = w0 * t.a.y; out[2] = w0 * t.a.z; out[3] = w0 * t.a.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[c] += __shfl_xor_sync(kFull, out[c], 2);
+  } else {
+    out[0] = w0 * t.a.x; out[1] = w0 * t.a.y; out[2] = w0 * t.a.z; out[3] = w0 * t.a.w;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      out[c] += __shfl_xor_sync(kFull, out[c], 1);
+      out[c] += __shfl_xor_sync(kFull, out[c], 2);
+    }
+  }
+}
+
+// One VM group (space plane x second factor) of one field for one sample.
+//   ia/fa, ib/fb : texel index / fraction along the plane's x and y axes; ic/fc along the second factor's axis
+//   it/ft        : keyframe row / fraction (dynamic) -- per-ray constants
+template <int C, bool DYN>
+struct GroupTaps {
+  Taps<C, true> sp;
+  Taps<C, DYN> se;
+};
+
+template <int C, bool DYN>
+__device__ __forceinline__ void group_fetch(GroupTaps<C, DYN>& g, const PlaneTab& T, int ia, int ib, int ic, int it, int xt,
+                                            int alt, bool ok) {
+  int so, eo;
+  if constexpr (C == 8) {
+    so = ((ib * T.W + ia + xt) << 3) + (alt << 2);
+    eo = ((it * T.L + ic + xt) << 3) + (alt << 2);
+  } else {
+    so = ((ib + alt) * T.W + ia + xt) << 2;
+    eo = ((DYN ? (it + alt) : 0) * T.L + ic + xt) << 2;
+  }
+  so = ok ? so : 0;
+  eo = ok ? eo : 0;
+  fetch<C, true>(g.sp, T.space, so, T.W * C);
+  fetch<C, DYN>(g.se, T.second, eo, T.L * C);
+}
+
+// -> prod[4] = space_c * second_c for this lane's channels (C==8: own half; C==4: all, replicated)
+template <int C, bool DYN>
+__device__ __forceinline__ void group_products(const GroupTaps<C, DYN>& g, float fa, float fb, float fc, float ft, int xt,
+                                               int alt, float (&prod)[4]) {
+  const float wa = xt ? fa : 1.0f - fa;
+  const float wc = xt ? fc : 1.0f - fc;
+  float A[4], B[4];
+  if constexpr (C == 8) {
+    interp<C, true>(g.sp, wa * (1.0f - fb), wa * fb, A);
+    interp<C, DYN>(g.se, DYN ? wc * (1.0f - ft) : wc, wc * ft, B);
+  } else {
+    interp<C, true>(g.sp, wa * (alt ? fb : 1.0f - fb), 0.0f, A);
+    interp<C, DYN>(g.se, wc * (DYN ? (alt ? ft : 1.0f - ft) : (alt ? 0.0f : 1.0f)), 0.0f, B);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) prod[c] = A[c] * B[c];
 }
 
 template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool STAGES>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (C1 + C2 == 0) ? 3 : 2)
 render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Derived dv,
               const __grid_constant__ RenderTabs tabs, const float* __restrict__ rays,
               const float* __restrict__ heads, float* __restrict__ rgb_out, long long n_rays, StageOut so) {
   constexpr int NT = C0 + C1 + C2;
   constexpr int ROWS = (SHADE == HR_SHADE_SH) ? 9 : 1;
   constexpr int ROUNDS = 4 * SPL;
-  extern __shared__ float smem[];
-  float* s_basis = smem;  // [3][BS]
-  const int BS = basis_block_stride(ROWS, NT);
-  for (int i = threadIdx.x; i < 3 * ROWS * NT; i += blockDim.x) {
-    int ch = i / (ROWS * NT), rem = i % (ROWS * NT);
-    s_basis[ch * BS + rem] = tabs.basis[i];
-  }
+  extern __shared__ float s_basis[];  // [app_dim][NT] copy of basis_mat
+  for (int i = threadIdx.x; i < 3 * ROWS * NT; i += blockDim.x) s_basis[i] = tabs.basis[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
   const int q = lane & 3, xt = q >> 1, alt = q & 1, quad = lane >> 2;
+  const int qc = min(q, 2);
   const int S = cfg.n_samples;
   const int out_stride = cfg.mlp_out;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
 
+  // Column of basis_mat feeding this lane's i-th product feature.  For an 8-channel group the lane holds
+  // [own half | other half]; 4-channel groups are replicated in natural order.
+  int fcol[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) fcol[i] = i;
+  if constexpr (C0 == 8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { fcol[i] = alt * 4 + i; fcol[4 + i] = (1 - alt) * 4 + i; }
+  }
+  if constexpr (C1 == 8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { fcol[C0 + i] = C0 + alt * 4 + i; fcol[C0 + 4 + i] = C0 + (1 - alt) * 4 + i; }
+  }
+  if constexpr (C2 == 8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { fcol[C0 + C1 + i] = C0 + C1 + alt * 4 + i; fcol[C0 + C1 + 4 + i] = C0 + C1 + (1 - alt) * 4 + i; }
+  }
+  float G[NT];  // per-lane row of the (view-folded) appearance matrix: rgb_q = act(sum_i G[i] * f[i])
+  if constexpr (SHADE == HR_SHADE_RGB) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) G[i] = s_basis[qc * NT + fcol[i]];
+  }
+
+  const float inv_x = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[3], cfg.aabb[0]));  // invaabbSize (tensorf_base.py:292)
+  const float inv_y = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[4], cfg.aabb[1]));
+  const float inv_z = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[5], cfg.aabb[2]));
+  const int line_bytes = out_stride * 4;
+
   for (long long ray = warp0; ray < n_rays; ray += nwarps) {
     const float* r = rays + ray * cfg.c_in;
+    const float* hrow = heads + ray * (long long)out_stride;
+    // ---- warm L1 with the next ray's head row (1.9 KB) while this one is processed ----
+    {
+      const long long nxt = ray + nwarps;
+      if (nxt < n_rays) {
+        const char* p = reinterpret_cast<const char*>(heads + nxt * (long long)out_stride) + lane * 128;
+        if (lane * 128 < line_bytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+        if (lane == 31) asm volatile("prefetch.global.L1 [%0];" ::"l"(rays + nxt * cfg.c_in));
+      }
+    }
     const float ox = __ldg(r + 0), oy = __ldg(r + 1), oz = __ldg(r + 2);
     const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
     const float time = __ldg(r + cfg.c_in - 1);
-    const float* hrow = heads + ray * (long long)out_stride;
 
-    // ---- per-ray keyframe snap (utils/flow_utils.py:18-31) and time coordinate ----
-    float base_t = 0.0f, toff = 0.0f, tau = 0.0f;
+    // ---- raw head values of this lane's sample(s): all loads issued before any use ----
+    float hz[SPL][4], hfl[SPL][3], hsg[SPL], hsp[SPL], hof[SPL][3];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      const int s = lane + 32 * j;
+      const float* hp = hrow + ((s < S) ? s : 0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) hz[j][c] = (c < cfg.n_z) ? __ldg(hp + (cfg.off_z + c) * S) : 0.0f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) hfl[j][c] = cfg.use_flow ? __ldg(hp + (cfg.off_flow + c) * S) : 0.0f;
+      hsg[j] = (cfg.off_sigma >= 0) ? __ldg(hp + cfg.off_sigma * S) : 0.0f;
+      hsp[j] = (cfg.off_point_sigma >= 0) ? __ldg(hp + cfg.off_point_sigma * S) : 0.0f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) hof[j][c] = cfg.use_offset ? __ldg(hp + (cfg.off_offset + c) * S) : 0.0f;
+    }
+
+    // ---- per-ray keyframe snap (utils/flow_utils.py:18-31), time coordinate and keyframe row ----
+    float toff = 0.0f, ft = 0.0f;
+    int it = 0;
     if (DYN || cfg.use_flow) {
       float tt = __fmul_rn(time, dv.time_fac);
       tt = fminf(fmaxf(tt, 0.0f), dv.kf_max);
       tt = rintf(__fsub_rn(tt, 1e-5f));
-      base_t = __fmul_rn(tt, dv.time_inv_fac);
+      const float base_t = __fmul_rn(tt, dv.time_inv_fac);
       toff = __fsub_rn(time, base_t);
-      // normalize_time_coord (tensorf_dynamic.py:615-616)
-      tau = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(base_t, dv.time_scale), dv.time_offset), 2.0f), 1.0f);
+      if (DYN) {
+        // normalize_time_coord (tensorf_dynamic.py:615-616) then grid_sample's unnormalise over K rows
+        const float tau = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(base_t, dv.time_scale), dv.time_offset), 2.0f), 1.0f);
+        const float iy = __fmul_rn(__fmul_rn(__fadd_rn(tau, 1.0f), 0.5f), (float)(dv.kt - 1));
+        it = max(0, min((int)floorf(iy), dv.kt - 2));
+        ft = iy - (float)it;
+      }
     }
 
-    float tkey[SPL];
-    float cs[SPL][3], csh[SPL][3], padd[SPL][3];  // colour scale/shift, total point displacement
+    // ---- view-dependent appearance matrix: G[q][i] = sum_k Y_k(dir) * basis[(q*9+k)][i]  (tensorf_utils.py:334-338)
+    if constexpr (SHADE == HR_SHADE_SH) {
+      float Y[9];
+      sh_basis9(dx, dy, dz, Y);  // viewdirs = rays[:,3:6] as given (point.py:866-867)
+      // the 3*NT entries are built once, spread over the lanes, then every lane collects its row in its column order
+      constexpr int GE = 3 * NT, GM = (GE + 31) / 32;
+      float g[GM];
+#pragma unroll
+      for (int m = 0; m < GM; ++m) {
+        const int e = min(lane + 32 * m, GE - 1);
+        const int eq = e / NT, ei = e % NT;
+        float a = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a = fmaf(Y[k], s_basis[(eq * 9 + k) * NT + ei], a);
+        g[m] = a;
+      }
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        const int E = qc * NT + fcol[i];
+        float v = 0.0f;
+#pragma unroll
+        for (int m = 0; m < GM; ++m) {
+          const float t = __shfl_sync(kFull, g[m], E & 31);
+          if ((E >> 5) == m) v = t;
+        }
+        G[i] = v;
+      }
+    }
+
+    // ---- lane = sample: intersection (base.py:155-203) ----
+    float tkey[SPL], disp[SPL][3];
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
       const int s = lane + 32 * j;
       const bool act = s < S;
-      auto H = [&](int c) -> float { return act ? __ldg(hrow + c * S + s) : 0.0f; };
-      float sg = 0.0f, sgp = 0.0f;
-      if (cfg.off_sigma >= 0) sg = apply_act(cfg.act_sigma, H(cfg.off_sigma));
-      if (cfg.off_point_sigma >= 0) sgp = apply_act(cfg.act_point_sigma, H(cfg.off_point_sigma));
-      auto density = [&](int off) -> float {
-        return (off < 0) ? 0.0f : ((off == cfg.off_sigma) ? sg : sgp);
-      };
-      // ---- intersection (base.py:155-203) ----
-      const float one_m = __fsub_rn(1.0f, cfg.isect_use_sigma ? density(cfg.isect_density_off) : 0.0f);
+      const float sg = (cfg.off_sigma >= 0) ? apply_act(cfg.act_sigma, hsg[j]) : 0.0f;
+      const float sgp = (cfg.off_point_sigma >= 0) ? apply_act(cfg.act_point_sigma, hsp[j]) : 0.0f;
+      const float dens_i = (cfg.isect_density_off < 0) ? 0.0f : ((cfg.isect_density_off == cfg.off_sigma) ? sg : sgp);
+      const float dens_o = (cfg.offset_density_off < 0) ? 0.0f : ((cfg.offset_density_off == cfg.off_sigma) ? sg : sgp);
+      const float one_m = __fsub_rn(1.0f, cfg.isect_use_sigma ? dens_i : 0.0f);
+      const float samp = cfg.samples[act ? s : 0];
       float t;
       if (cfg.isect_type == HR_ISECT_Z_PLANE) {
-        float zr = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, H(cfg.off_z))), one_m);
-        float z = __fadd_rn(__fmul_rn(zr, cfg.z_scale), cfg.samples[act ? s : 0]);
+        float zr = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, hz[j][0])), one_m);
+        float z = __fadd_rn(__fmul_rn(zr, cfg.z_scale), samp);
         if (cfg.contract_samples) z = inv_contract_distance(cfg, dv, z);
         float dzg = (fabsf(dz) < 1e-5f) ? 1e12f : dz;  // intersect_utils.py:135-142
         t = __fdiv_rn(__fsub_rn(z, oz), dzg);
       } else {
         float zc[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          zc[c] = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, H(cfg.off_z + c))), one_m);
+        for (int c = 0; c < 4; ++c) zc[c] = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, hz[j][c])), one_m);
         // primitive.py:410-418
         float gx = __fadd_rn(__fmul_rn(zc[0], cfg.sphere_origin_scale), cfg.sphere_origin_initial[0]);
         float gy = __fadd_rn(__fmul_rn(zc[1], cfg.sphere_origin_scale), cfg.sphere_origin_initial[1]);
         float gz = __fadd_rn(__fmul_rn(zc[2], cfg.sphere_origin_scale), cfg.sphere_origin_initial[2]);
-        float rad = __fadd_rn(__fmul_rn(zc[3], cfg.z_scale), cfg.samples[act ? s : 0]);
+        float rad = __fadd_rn(__fmul_rn(zc[3], cfg.z_scale), samp);
         if (cfg.contract_samples) rad = inv_contract_distance(cfg, dv, rad);
         // primitive.py:420-438 + intersect_utils.py:45-84
         float sox = __fmul_rn(ox, gx), soy = __fmul_rn(oy, gy), soz = __fmul_rn(oz, gz);
@@ -262,37 +353,23 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       }
       if ((t <= cfg.isect_near) || (t >= cfg.isect_far)) t = 0.0f;
       tkey[j] = act ? t : __int_as_float(0x7f800000);
-
-      // ---- per-sample point displacement: flow * dt (point.py:816-820) + offset (point.py:383-391) ----
-      padd[j][0] = padd[j][1] = padd[j][2] = 0.0f;
-      float fl[3] = {0.f, 0.f, 0.f}, of[3] = {0.f, 0.f, 0.f};
-      if (cfg.use_flow) {
+      // per-sample displacement applied after the points are formed: flow * dt (point.py:816-820), then
+      // offset * (1 - sigma) (point.py:383-391) -- kept as two addends to preserve the reference's rounding order
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          fl[c] = __fmul_rn(apply_act(cfg.flow_act, apply_act(cfg.act_flow, H(cfg.off_flow + c))), toff);
-      }
-      if (cfg.use_offset) {
-        float om = __fsub_rn(1.0f, density(cfg.offset_density_off));
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          of[c] = __fmul_rn(apply_act(cfg.offset_act, apply_act(cfg.act_offset, H(cfg.off_offset + c))), om);
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { padd[j][c] = fl[c]; cs[j][c] = of[c]; }
-      // (of[] parked in cs[] until the points are formed; overwritten by the colour heads below)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) csh[j][c] = 0.0f;
-      if (cfg.use_color_scale_shift) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) csh[j][c] = apply_act(cfg.act_cshift, H(cfg.off_cshift + c));
+      for (int c = 0; c < 3; ++c) {
+        disp[j][c] = cfg.use_flow ? __fmul_rn(apply_act(cfg.flow_act, apply_act(cfg.act_flow, hfl[j][c])), toff) : 0.0f;
+        hof[j][c] = cfg.use_offset
+                        ? __fmul_rn(apply_act(cfg.offset_act, apply_act(cfg.act_offset, hof[j][c])), __fsub_rn(1.0f, dens_o))
+                        : 0.0f;
       }
     }
 
     // ---- sort distances only (base.py:206-210) ----
     if (cfg.isect_sort) sort_keys<SPL>(tkey, lane);
 
-    // ---- points, contraction, flow, offset, validity, normalised coordinates ----
-    float dist[SPL], un[SPL][3];
+    // ---- points, contraction, flow, offset, validity, texel coordinates along the three grid axes ----
+    float dist[SPL], fx[SPL], fy[SPL], fz[SPL];
+    int ix[SPL], iy[SPL], iz[SPL];  // ix < 0 flags an invalid sample
     bool valid[SPL];
     float cocx = ox, cocy = oy, cocz = oz;
     if (cfg.contract_type == HR_CONTRACT_MIPNERF) contract_point(cfg, dv, cocx, cocy, cocz);
@@ -302,7 +379,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       const bool act = s < S;
       float t = act ? tkey[j] : 0.0f;
       const bool zero = (t == 0.0f);
-      float px = __fadd_rn(ox, __fmul_rn(dx, t));
+      float px = __fadd_rn(ox, __fmul_rn(dx, t));  // base.py:226
       float py = __fadd_rn(oy, __fmul_rn(dy, t));
       float pz = __fadd_rn(oz, __fmul_rn(dz, t));
       if (cfg.contract_type == HR_CONTRACT_MIPNERF) {  // base.py:242-246, contract.py:43-50
@@ -311,19 +388,30 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         t = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
         if (zero) t = 0.0f;
       }
-      // flow then offset (two separate adds in the reference)
-      px = __fadd_rn(__fadd_rn(px, padd[j][0]), cs[j][0]);
-      py = __fadd_rn(__fadd_rn(py, padd[j][1]), cs[j][1]);
-      pz = __fadd_rn(__fadd_rn(pz, padd[j][2]), cs[j][2]);
+      px = __fadd_rn(__fadd_rn(px, disp[j][0]), hof[j][0]);
+      py = __fadd_rn(__fadd_rn(py, disp[j][1]), hof[j][1]);
+      pz = __fadd_rn(__fadd_rn(pz, disp[j][2]), hof[j][2]);
       dist[j] = t;
       // valid_mask (tensorf_base.py:349-353) & distance > 0 (tensorf_dynamic.py:690)
-      bool inside = !((cfg.aabb[0] > px) || (px > cfg.aabb[3]) || (cfg.aabb[1] > py) || (py > cfg.aabb[4]) ||
-                      (cfg.aabb[2] > pz) || (pz > cfg.aabb[5]));
+      const bool inside = !((cfg.aabb[0] > px) || (px > cfg.aabb[3]) || (cfg.aabb[1] > py) || (py > cfg.aabb[4]) ||
+                            (cfg.aabb[2] > pz) || (pz > cfg.aabb[5]));
       valid[j] = act && inside && (t > 0.0f);
-      // normalize_coord (tensorf_base.py:308-309)
-      un[j][0] = __fsub_rn(__fmul_rn(__fsub_rn(px, cfg.aabb[0]), __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[3], cfg.aabb[0]))), 1.0f);
-      un[j][1] = __fsub_rn(__fmul_rn(__fsub_rn(py, cfg.aabb[1]), __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[4], cfg.aabb[1]))), 1.0f);
-      un[j][2] = __fsub_rn(__fmul_rn(__fsub_rn(pz, cfg.aabb[2]), __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[5], cfg.aabb[2]))), 1.0f);
+      // normalize_coord (tensorf_base.py:308-309), then grid_sample's align_corners=True unnormalise
+      // ((u+1)/2)*(size-1) along each grid axis; index clamped to [0,size-2] with the fraction recomputed, which is
+      // exact for in-range points (the out-of-range neighbour of a point on the max face has weight 0).
+      const float ux = __fsub_rn(__fmul_rn(__fsub_rn(px, cfg.aabb[0]), inv_x), 1.0f);
+      const float uy = __fsub_rn(__fmul_rn(__fsub_rn(py, cfg.aabb[1]), inv_y), 1.0f);
+      const float uz = __fsub_rn(__fmul_rn(__fsub_rn(pz, cfg.aabb[2]), inv_z), 1.0f);
+      const float tx = __fmul_rn(__fmul_rn(__fadd_rn(ux, 1.0f), 0.5f), (float)(dv.res[0] - 1));
+      const float ty = __fmul_rn(__fmul_rn(__fadd_rn(uy, 1.0f), 0.5f), (float)(dv.res[1] - 1));
+      const float tz = __fmul_rn(__fmul_rn(__fadd_rn(uz, 1.0f), 0.5f), (float)(dv.res[2] - 1));
+      ix[j] = max(0, min((int)floorf(tx), dv.res[0] - 2));
+      iy[j] = max(0, min((int)floorf(ty), dv.res[1] - 2));
+      iz[j] = max(0, min((int)floorf(tz), dv.res[2] - 2));
+      fx[j] = tx - (float)ix[j];
+      fy[j] = ty - (float)iy[j];
+      fz[j] = tz - (float)iz[j];
+      if (!valid[j]) ix[j] = -1;
       if (STAGES && act) {
         if (so.distances) so.distances[ray * S + s] = t;
         if (so.points) {
@@ -332,144 +420,91 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
           so.points[(ray * S + s) * 3 + 2] = pz;
         }
       }
-      // colour scale head (needed only at the end)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) cs[j][c] = 0.0f;
-      if (cfg.use_color_scale_shift) {
-        const float* hp = hrow + s;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) cs[j][c] = act ? apply_act(cfg.act_cscale, __ldg(hp + (cfg.off_cscale + c) * S)) : 0.0f;
-      }
     }
 
-    // ---- VM gather, 8 samples per round, 4 lanes per sample ----
-    float sig_r[ROUNDS];  // sigma feature of (round, quad), replicated in the quad
-    float rgb_r[ROUNDS];  // shaded colour channel q of (round, quad) (lanes q<3)
-    float Y[9];
-    if constexpr (SHADE == HR_SHADE_SH) sh_basis9(dx, dy, dz, Y);  // viewdirs = rays[:,3:6] as given (point.py:866-867)
-    const int qc = min(q, 2);
+    // ---- VM gather: 8 samples per round, 4 lanes per sample (matMode [[0,1],[0,2],[1,2]], vecMode [2,1,0]) ----
+    float sig_r[ROUNDS];  // density feature of (round, quad), replicated in the quad
+    float rgb_r[ROUNDS];  // shaded colour channel q of (round, quad)
 #pragma unroll
     for (int rd = 0; rd < ROUNDS; ++rd) {
-      const int j = rd >> 2;
-      const int src = (rd & 3) * 8 + quad;
-      const float u0 = __shfl_sync(kFull, un[j][0], src);
-      const float u1 = __shfl_sync(kFull, un[j][1], src);
-      const float u2 = __shfl_sync(kFull, un[j][2], src);
-      const bool ok = __shfl_sync(kFull, valid[j] ? 1 : 0, src) != 0;
       sig_r[rd] = 0.0f;
       rgb_r[rd] = 0.0f;
       if (rd * 8 >= S) continue;  // warp-uniform
-      // matMode = [[0,1],[0,2],[1,2]], vecMode / time axis = [2,1,0]
-      TapSet<C0> s0s, s0t, a0s, a0t;
-      TapSet<(C1 ? C1 : 4)> s1s, s1t, a1s, a1t;
-      TapSet<(C2 ? C2 : 4)> s2s, s2t, a2s, a2t;
-      issue<C0>(s0s, tabs.sig[0].space, tabs.sig[0].H, tabs.sig[0].W, u0, u1, xt, alt, ok);
-      issue<C0>(s0t, tabs.sig[0].second, tabs.sig[0].H2, tabs.sig[0].L, u2, tau, xt, alt, ok);
-      issue<C0>(a0s, tabs.app[0].space, tabs.app[0].H, tabs.app[0].W, u0, u1, xt, alt, ok);
-      issue<C0>(a0t, tabs.app[0].second, tabs.app[0].H2, tabs.app[0].L, u2, tau, xt, alt, ok);
+      const int j = rd >> 2;
+      const int src = (rd & 3) * 8 + quad;
+      int sx = __shfl_sync(kFull, ix[j], src);
+      const int sy = __shfl_sync(kFull, iy[j], src);
+      const int sz = __shfl_sync(kFull, iz[j], src);
+      const float gx = __shfl_sync(kFull, fx[j], src);
+      const float gy = __shfl_sync(kFull, fy[j], src);
+      const float gz = __shfl_sync(kFull, fz[j], src);
+      const bool ok = sx >= 0;
+      sx = max(sx, 0);
+      GroupTaps<C0, DYN> s0, a0;
+      GroupTaps<(C1 ? C1 : 4), DYN> s1, a1;
+      GroupTaps<(C2 ? C2 : 4), DYN> s2, a2;
+      group_fetch<C0, DYN>(s0, tabs.sig[0], sx, sy, sz, it, xt, alt, ok);
+      group_fetch<C0, DYN>(a0, tabs.app[0], sx, sy, sz, it, xt, alt, ok);
       if constexpr (C1 > 0) {
-        issue<C1>(s1s, tabs.sig[1].space, tabs.sig[1].H, tabs.sig[1].W, u0, u2, xt, alt, ok);
-        issue<C1>(s1t, tabs.sig[1].second, tabs.sig[1].H2, tabs.sig[1].L, u1, tau, xt, alt, ok);
-        issue<C1>(a1s, tabs.app[1].space, tabs.app[1].H, tabs.app[1].W, u0, u2, xt, alt, ok);
-        issue<C1>(a1t, tabs.app[1].second, tabs.app[1].H2, tabs.app[1].L, u1, tau, xt, alt, ok);
+        group_fetch<C1, DYN>(s1, tabs.sig[1], sx, sz, sy, it, xt, alt, ok);
+        group_fetch<C1, DYN>(a1, tabs.app[1], sx, sz, sy, it, xt, alt, ok);
       }
       if constexpr (C2 > 0) {
-        issue<C2>(s2s, tabs.sig[2].space, tabs.sig[2].H, tabs.sig[2].W, u1, u2, xt, alt, ok);
-        issue<C2>(s2t, tabs.sig[2].second, tabs.sig[2].H2, tabs.sig[2].L, u0, tau, xt, alt, ok);
-        issue<C2>(a2s, tabs.app[2].space, tabs.app[2].H, tabs.app[2].W, u1, u2, xt, alt, ok);
-        issue<C2>(a2t, tabs.app[2].second, tabs.app[2].H2, tabs.app[2].L, u0, tau, xt, alt, ok);
+        group_fetch<C2, DYN>(s2, tabs.sig[2], sy, sz, sx, it, xt, alt, ok);
+        group_fetch<C2, DYN>(a2, tabs.app[2], sy, sz, sx, it, xt, alt, ok);
       }
-      // ---- density feature: sum_c space_c * second_c over all groups (tensorf_dynamic.py:330) ----
-      float f[NT];  // appearance product features, torch.cat order over groups
-      float sf = 0.0f;
+      // density feature: sum_c space_c * second_c over all groups (tensorf_dynamic.py:330, tensorf_no_sample.py:76-78)
+      float f[NT];
+      float sf;
       {
-        float A[4], B[4];
-        combine<C0>(s0s, A);
-        combine<C0>(s0t, B);
-        float part = A[0] * B[0] + A[1] * B[1] + A[2] * B[2] + A[3] * B[3];
-        if constexpr (C0 == 8) part += __shfl_xor_sync(kFull, part, 1);
-        sf = part;
-        combine<C0>(a0s, A);
-        combine<C0>(a0t, B);
+        float p[4];
+        group_products<C0, DYN>(s0, gx, gy, gz, ft, xt, alt, p);
+        sf = (p[0] + p[1]) + (p[2] + p[3]);
+        if constexpr (C0 == 8) sf += __shfl_xor_sync(kFull, sf, 1);
+        group_products<C0, DYN>(a0, gx, gy, gz, ft, xt, alt, p);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) f[c] = p[c];
         if constexpr (C0 == 8) {
-          float mine[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) mine[c] = A[c] * B[c];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float oth = __shfl_xor_sync(kFull, mine[c], 1);
-            f[c] = alt ? oth : mine[c];
-            f[4 + c] = alt ? mine[c] : oth;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) f[c] = A[c] * B[c];
+          for (int c = 0; c < 4; ++c) f[4 + c] = __shfl_xor_sync(kFull, p[c], 1);
         }
       }
       if constexpr (C1 > 0) {
-        float A[4], B[4];
-        combine<(C1 ? C1 : 4)>(s1s, A);
-        combine<(C1 ? C1 : 4)>(s1t, B);
-        float part = A[0] * B[0] + A[1] * B[1] + A[2] * B[2] + A[3] * B[3];
+        float p[4];
+        group_products<C1, DYN>(s1, gx, gz, gy, ft, xt, alt, p);
+        float part = (p[0] + p[1]) + (p[2] + p[3]);
         if constexpr (C1 == 8) part += __shfl_xor_sync(kFull, part, 1);
         sf += part;
-        combine<(C1 ? C1 : 4)>(a1s, A);
-        combine<(C1 ? C1 : 4)>(a1t, B);
+        group_products<C1, DYN>(a1, gx, gz, gy, ft, xt, alt, p);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) f[C0 + c] = p[c];
         if constexpr (C1 == 8) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float m = A[c] * B[c];
-            float oth = __shfl_xor_sync(kFull, m, 1);
-            f[C0 + c] = alt ? oth : m;
-            f[C0 + 4 + c] = alt ? m : oth;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) f[C0 + c] = A[c] * B[c];
+          for (int c = 0; c < 4; ++c) f[C0 + 4 + c] = __shfl_xor_sync(kFull, p[c], 1);
         }
       }
       if constexpr (C2 > 0) {
-        float A[4], B[4];
-        combine<(C2 ? C2 : 4)>(s2s, A);
-        combine<(C2 ? C2 : 4)>(s2t, B);
-        float part = A[0] * B[0] + A[1] * B[1] + A[2] * B[2] + A[3] * B[3];
+        float p[4];
+        group_products<C2, DYN>(s2, gy, gz, gx, ft, xt, alt, p);
+        float part = (p[0] + p[1]) + (p[2] + p[3]);
         if constexpr (C2 == 8) part += __shfl_xor_sync(kFull, part, 1);
         sf += part;
-        combine<(C2 ? C2 : 4)>(a2s, A);
-        combine<(C2 ? C2 : 4)>(a2t, B);
+        group_products<C2, DYN>(a2, gy, gz, gx, ft, xt, alt, p);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) f[C0 + C1 + c] = p[c];
         if constexpr (C2 == 8) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float m = A[c] * B[c];
-            float oth = __shfl_xor_sync(kFull, m, 1);
-            f[C0 + C1 + c] = alt ? oth : m;
-            f[C0 + C1 + 4 + c] = alt ? m : oth;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) f[C0 + C1 + c] = A[c] * B[c];
+          for (int c = 0; c < 4; ++c) f[C0 + C1 + 4 + c] = __shfl_xor_sync(kFull, p[c], 1);
         }
       }
       sig_r[rd] = ok ? sf : 0.0f;
-      // ---- appearance: basis_mat (tensorf_dynamic.py:371) + shading (tensorf_utils.py:334-343) ----
-      const float* bq = s_basis + qc * BS;
+      // appearance: basis_mat (tensorf_dynamic.py:371) folded with the shading (tensorf_utils.py:334-343)
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NT; ++i) acc = fmaf(G[i], f[i], acc);
       float col;
-      if constexpr (SHADE == HR_SHADE_SH) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          float F = 0.0f;
-#pragma unroll
-          for (int i = 0; i < NT; ++i) F = fmaf(bq[k * NT + i], f[i], F);
-          acc = fmaf(Y[k], F, acc);
-        }
-        col = fmaxf(acc + 0.5f, 0.0f);
-      } else {
-        float F = 0.0f;
-#pragma unroll
-        for (int i = 0; i < NT; ++i) F = fmaf(bq[i], f[i], F);
-        col = 1.0f / (1.0f + expf(-F));
-      }
+      if constexpr (SHADE == HR_SHADE_SH) col = fmaxf(acc + 0.5f, 0.0f);
+      else col = 1.0f / (1.0f + expf(-acc));
       rgb_r[rd] = ok ? col : 0.0f;
     }
 
@@ -477,9 +512,19 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     float wgt[SPL];
     float carryT = 1.0f;
     float accw = 0.0f, accB[3] = {0.f, 0.f, 0.f};
+    float csA[SPL][3];
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
       const int s = lane + 32 * j;
+      const float* hp = hrow + ((s < S) ? s : 0);
+      float cs_raw[3] = {0.f, 0.f, 0.f}, csh_raw[3] = {0.f, 0.f, 0.f};
+      if (cfg.use_color_scale_shift) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          cs_raw[c] = __ldg(hp + (cfg.off_cscale + c) * S);
+          csh_raw[c] = __ldg(hp + (cfg.off_cshift + c) * S);
+        }
+      }
       float feat = 0.0f;
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
@@ -506,8 +551,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       if (s >= S) alpha = 0.0f;
       float a1 = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
       if (s >= S) a1 = 1.0f;
-      // inclusive product scan
-      float inc = a1;
+      float inc = a1;  // inclusive product scan
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         float o = __shfl_up_sync(kFull, inc, d);
@@ -515,31 +559,36 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       }
       float exc = __shfl_up_sync(kFull, inc, 1);
       if (lane == 0) exc = 1.0f;
-      float T = carryT * exc;
+      const float T = carryT * exc;
       carryT = carryT * __shfl_sync(kFull, inc, 31);
-      float w = alpha * T;
+      const float w = alpha * T;
       wgt[j] = w;
       if (STAGES && s < S) {
         if (so.sigma) so.sigma[ray * S + s] = sigma;
         if (so.weights) so.weights[ray * S + s] = w;
       }
       accw += w;
+      const float m = (w > cfg.weight_thre) ? w : 0.0f;  // app_mask (tensorf_dynamic.py:750)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) accB[c] += w * csh[j][c];
+      for (int c = 0; c < 3; ++c) {
+        const float csv = cfg.use_color_scale_shift ? apply_act(cfg.act_cscale, cs_raw[c]) : 0.0f;
+        const float cshv = cfg.use_color_scale_shift ? apply_act(cfg.act_cshift, csh_raw[c]) : 0.0f;
+        csA[j][c] = (s < S) ? m * (csv + 1.0f) : 0.0f;
+        accB[c] += (s < S) ? w * cshv : 0.0f;
+      }
     }
 
     // ---- composite: sum_s w_s * (rgb_s*(1+cs_s) + csh_s) (tensorf_dynamic.py:780-792) ----
     float accq = 0.0f;
 #pragma unroll
     for (int rd = 0; rd < ROUNDS; ++rd) {
+      if (rd * 8 >= S) continue;
       const int j = rd >> 2;
       const int src = (rd & 3) * 8 + quad;
-      float m = (wgt[j] > cfg.weight_thre) ? wgt[j] : 0.0f;  // app_mask (tensorf_dynamic.py:750)
-      float A0 = m * (cs[j][0] + 1.0f), A1 = m * (cs[j][1] + 1.0f), A2 = m * (cs[j][2] + 1.0f);
-      float g0 = __shfl_sync(kFull, A0, src);
-      float g1 = __shfl_sync(kFull, A1, src);
-      float g2 = __shfl_sync(kFull, A2, src);
-      float Aq = (q == 0) ? g0 : ((q == 1) ? g1 : g2);
+      const float g0 = __shfl_sync(kFull, csA[j][0], src);
+      const float g1 = __shfl_sync(kFull, csA[j][1], src);
+      const float g2 = __shfl_sync(kFull, csA[j][2], src);
+      const float Aq = (q == 0) ? g0 : ((q == 1) ? g1 : g2);
       accq = fmaf(Aq, rgb_r[rd], accq);
     }
 #pragma unroll
@@ -566,9 +615,9 @@ static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const Ren
                               cudaStream_t stream) {
   constexpr int ROWS = (SHADE == HR_SHADE_SH) ? 9 : 1;
   constexpr int NT = C0 + C1 + C2;
-  size_t smem = 3 * (size_t)basis_block_stride(ROWS, NT) * sizeof(float);
+  size_t smem = 3 * (size_t)ROWS * NT * sizeof(float);
   long long ctas_needed = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-  long long grid = ctas_needed < (long long)num_sms * 16 ? ctas_needed : (long long)num_sms * 16;
+  long long grid = ctas_needed < (long long)num_sms * kMinCtasPerSm * 2 ? ctas_needed : (long long)num_sms * kMinCtasPerSm * 2;
   if (grid < 1) grid = 1;
   if (so) {
     render_kernel<SPL, DYN, C0, C1, C2, SHADE, true><<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(

@@ -1,0 +1,158 @@
+"""Host-side logic that needs no GPU: config lowering, registry surface, chunk loop, state_dict layout,
+C-ABI symbol table."""
+import os
+import re
+
+import pytest
+import torch
+
+import hyperreel_b200 as hb
+from hyperreel_b200 import lib as L
+from hyperreel_b200.signature import UnsupportedPipeline, lower
+from hyperreel_b200.state import n_to_reso, seeded_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "hyperreel_b200.h")).read()
+    declared = set(re.findall(r"\b(hr_[a-z_]+)\s*\(", header))
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    lib = L.load_library()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.hr_abi_version() == L.HR_ABI_VERSION
+    m = re.search(r"#define HR_ABI_VERSION (\d+)", header)
+    assert int(m.group(1)) == L.HR_ABI_VERSION
+
+
+def test_ctypes_struct_matches_header_field_order():
+    header = open(os.path.join(ROOT, "include", "hyperreel_b200.h")).read()
+    body = header[header.index("typedef struct hr_config {"):header.index("} hr_config;")]
+    fields = []
+    for line in body.splitlines()[1:]:
+        line = line.split("/*")[0].strip()
+        if not line or line.startswith("*") or line.startswith("//"):
+            continue
+        decl = line.rstrip(";")
+        names = decl.split(None, 1)[1] if " " in decl else ""
+        for n in names.split(","):
+            n = re.sub(r"\[.*\]", "", n).strip()
+            if n:
+                fields.append(n)
+    assert fields == [f[0] for f in L.hr_config._fields_]
+
+
+def test_create_without_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg, ds = hb.configs.get("technicolor_z_plane", n_voxels=16 ** 3)
+    model = hb.LightfieldModel(cfg, dataset=ds)
+    model.eval()
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(4, 8))  # CPU rays: no fallback
+    import ctypes as C
+    h = C.c_void_p()
+    rc = model._lib.hr_create(C.byref(model.sig.cfg), 0, C.byref(h))
+    assert rc != 0 and b"no CUDA device" in model._lib.hr_last_error()
+
+
+def test_lowering_technicolor():
+    cfg, ds = hb.configs.get("technicolor_z_plane")
+    sig = lower(cfg, ds)
+    c = sig.cfg
+    assert (c.c_in, c.mlp_in, c.mlp_width, c.mlp_layers, c.mlp_skip, c.mlp_out) == (8, 9, 256, 6, 3, 480)
+    assert sig.mlp_layer_shapes == [(256, 9), (256, 256), (256, 256), (256, 265), (256, 256), (480, 256)]
+    assert sig.head_names == ["z_vals", "spatial_flow", "sigma", "point_sigma", "point_offset", "color_scale", "color_shift"]
+    assert (c.off_z, c.off_flow, c.off_sigma, c.off_point_sigma, c.off_offset, c.off_cscale, c.off_cshift) == (0, 1, 4, 5, 6, 9, 12)
+    assert c.act_sigma.kind == L.ACT_SIGMOID and c.act_sigma.shift == 4.0
+    assert c.act_flow.outer_fac == 0.25 and c.flow_act.outer_fac == 0.25  # the 0.25 factor is applied twice
+    assert c.act_offset.kind == L.ACT_TANH and c.act_offset.outer_fac == 0.25
+    assert c.isect_act.outer_fac == 0.5 and c.isect_density_off == 4 and c.offset_density_off == 5
+    assert abs(c.z_scale - 2.0 / 31.0) < 1e-6 and c.samples[0] == -1.0 and c.samples[31] == 1.0
+    assert c.dynamic == 1 and c.num_keyframes == 12 and c.num_frames == 50
+    assert list(c.n_sigma) == [8, 0, 0] and c.shading == L.SHADE_SH and c.app_dim == 27
+    assert c.distance_scale == 16.0 and c.weight_thre == 0.0 and c.use_color_scale_shift == 1
+
+
+def test_lowering_donerf_uses_dataset_bounds_and_sigma_for_offset():
+    cfg, ds = hb.configs.get("donerf_sphere")
+    c = lower(cfg, ds).cfg
+    assert c.c_in == 6 and c.mlp_in == 18 and c.n_z == 4 and c.isect_type == L.ISECT_SPHERE
+    assert c.isect_near == 0.5 and c.contract_type == L.CONTRACT_MIPNERF and c.contract_samples == 1
+    assert c.contract_start_radius == 1.0 and c.contract_end_radius == 15.0
+    assert c.offset_density_off == c.off_sigma  # point_offset_0 has no in_density_field -> 'sigma'
+    assert c.dynamic == 0 and c.shading == L.SHADE_RGB and list(c.n_sigma) == [8, 4, 4]
+
+
+def test_unsupported_pipelines_raise():
+    cfg, ds = hb.configs.get("technicolor_z_plane")
+    bad = hb.to_cfg(hb.config.to_plain(cfg))
+    bad.embedding.embeddings.ray_intersect_0.intersect.type = "cylinder"
+    with pytest.raises(UnsupportedPipeline):
+        lower(bad, ds)
+    bad = hb.to_cfg(hb.config.to_plain(cfg))
+    bad.color.net.shadingMode = "MLP_Fea"
+    with pytest.raises(UnsupportedPipeline):
+        lower(bad, ds)
+    bad = hb.to_cfg(hb.config.to_plain(cfg))
+    bad.embedding.embeddings.ray_prediction_0.outputs.sigma.activation.window_epochs = 10 ** 9
+    with pytest.raises(UnsupportedPipeline):
+        lower(bad, ds, cur_iter=5, iters_per_epoch=4000)  # EaseValue still easing at iteration 5
+    bad = hb.to_cfg(hb.config.to_plain(cfg))
+    bad.embedding.embeddings.ray_prediction_0.params.ray.param.fn = "spherical"
+    with pytest.raises(UnsupportedPipeline):
+        lower(bad, ds)
+
+
+def test_epochs_to_iters_rewrite():
+    c = hb.to_cfg({"a": {"window_epochs": 3, "wait_epochs": 1, "x": {"max_freq_epoch": 2}}, "l": [{"stop_epochs": 4}]})
+    hb.epochs_to_iters(c, 4000)
+    assert c.a.window_iters == 12000 and c.a.wait_iters == 4000 and c.a.x.max_freq_iter == 8000 and c.l[0].stop_iters == 16000
+
+
+def test_state_dict_names_follow_reference_layout():
+    cfg, ds = hb.configs.get("technicolor_z_plane", n_voxels=32 ** 3)
+    sig = lower(cfg, ds)
+    sd = seeded_state_dict(sig, seed=0)
+    assert sd["model.embedding_model.embeddings.0.net.layers.3.0.weight"].shape == (256, 265)
+    assert sd["model.embedding_model.embeddings.0.net.layers.5.weight"].shape == (480, 256)
+    assert sd["model.color_model.net.density_plane_space.0"].shape == (1, 8, 40, 40)
+    assert sd["model.color_model.net.density_plane_space.1"].shape == (1, 0, 20, 40)
+    assert sd["model.color_model.net.density_plane_time.0"].shape == (1, 8, 12, 20)
+    assert sd["model.color_model.net.basis_mat.weight"].shape == (27, 8)
+    assert sd["model.color_model.net.gridSize"].tolist() == [40, 40, 20]
+    cfg, ds = hb.configs.get("donerf_sphere", n_voxels=32 ** 3)
+    sd = seeded_state_dict(lower(cfg, ds), seed=0)
+    assert sd["model.color_model.net.density_line.1"].shape == (1, 4, 32, 1)
+    assert sd["model.color_model.net.app_plane.2"].shape == (1, 4, 32, 32)
+
+
+def test_final_grid_sizes_match_survey():
+    assert n_to_reso(512000000, torch.tensor([[-2.0, -2.0, -1.0], [2.0, 2.0, 1.0]])) == [1007, 1007, 503]
+    assert n_to_reso(216000000, torch.tensor([[-2.0, -2.0, -2.0], [2.0, 2.0, 2.0]])) == [600, 600, 600]
+    assert n_to_reso(262144000, torch.tensor([[-2.0, -1.5, -1.25], [2.0, 1.5, 1.25]])) == [823, 617, 514]
+
+
+def test_render_chunked_is_chunk_invariant_with_any_render_fn():
+    def fake(rays, **kw):
+        return {"rgb": rays[:, :3] * 2.0 + 1.0, "aux": rays[:, 3:4]}
+    rays = torch.randn(1000, 8)
+    full = hb.render_chunked(rays, fake, {}, chunk=1 << 20)
+    for chunk in (1, 7, 333, 1000, 5000):
+        out = hb.render_chunked(rays, fake, {}, chunk=chunk)
+        assert torch.equal(out["rgb"], full["rgb"]) and torch.equal(out["aux"], full["aux"])
+
+
+def test_system_loads_shrunk_grid_checkpoint_shapes():
+    """load_state_dict re-creates the tables at the checkpoint's gridSize (nlf/__init__.py:448-463)."""
+    cfg, ds = hb.configs.get("donerf_sphere", n_voxels=16 ** 3)
+    system = hb.INRSystem(hb.to_cfg({"model": cfg, "training": {"ray_chunk": 64}, "dataset": ds}))
+    cfg2, _ = hb.configs.get("donerf_sphere", n_voxels=16 ** 3)
+    sig = lower(cfg2, ds)
+    sd = seeded_state_dict(sig, grid=[20, 12, 9], seed=3)
+    system.load_state_dict({"state_dict": {"render_fn." + k: v for k, v in sd.items()}})
+    net = system.render_fn.model.color_model.net
+    assert net.gridSize.tolist() == [20, 12, 9]
+    assert net.density_plane[1].shape == (1, 4, 9, 20) and net.app_line[2].shape == (1, 4, 20, 1)
+    assert torch.equal(net.density_plane[0].data, sd["model.color_model.net.density_plane.0"])

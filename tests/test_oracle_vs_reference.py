@@ -1,0 +1,60 @@
+"""Live pin: the oracle and the built-in configs against the reference checkout itself (skipped where
+/root/reference is absent, e.g. on the GPU box -- the committed golden vectors cover that case)."""
+import pytest
+import torch
+
+from oracle import ref_shim
+from oracle.hyperreel_oracle import HyperReelOracle
+from tests.cases import build_case
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference checkout not present")
+
+
+def _floatify(o):
+    if isinstance(o, dict):
+        return {k: _floatify(v) for k, v in o.items()}
+    if isinstance(o, list):
+        return [_floatify(v) for v in o]
+    if isinstance(o, str):
+        try:
+            return float(o)  # PyYAML 1.1 reads `1e-3` as a string
+        except ValueError:
+            return o
+    return o
+
+
+def _key_order(o):
+    if isinstance(o, dict):
+        return [(k, _key_order(v)) for k, v in o.items()]
+    if isinstance(o, list):
+        return [_key_order(v) for v in o]
+    return None
+
+
+@pytest.mark.parametrize("name", ["technicolor_z_plane", "neural_3d_z_plane", "donerf_sphere", "shiny_z_plane_tiny"])
+def test_builtin_config_equals_reference_yaml(name):
+    from hyperreel_b200 import configs
+    from hyperreel_b200.config import to_plain
+    ref = _floatify(ref_shim.load_reference_yaml(name))
+    mine = _floatify(to_plain(configs.BUILTIN[name]()))
+    assert ref == mine
+    # ordered sections: embedding order, head order and param-group order are semantic
+    e_ref, e_mine = ref["embedding"]["embeddings"], mine["embedding"]["embeddings"]
+    assert list(e_ref) == list(e_mine)
+    assert list(e_ref["ray_prediction_0"]["outputs"]) == list(e_mine["ray_prediction_0"]["outputs"])
+    assert list(e_ref["ray_prediction_0"]["params"]) == list(e_mine["ray_prediction_0"]["params"])
+
+
+@pytest.mark.parametrize("name", ["technicolor_trained", "neural3d_trained", "donerf_s16"])
+def test_oracle_matches_live_reference_on_fresh_rays(name):
+    case = build_case(name, n=777)
+    ref = ref_shim.build_reference(case.model_cfg_plain, case.dataset)
+    missing, unexpected = ref.load_state_dict(case.state_dict, strict=False)
+    assert not unexpected
+    out = ref_shim.run_reference(ref, case.rays.clone(), chunk=200, capture=True)
+    st = {}
+    rgb = HyperReelOracle(case.model_cfg_plain, case.dataset, case.state_dict).render(case.rays.clone(), st)
+    assert (rgb - out["rgb"]).abs().max() <= 2e-6
+    n, S = case.rays.shape[0], case.n_samples
+    assert (st["points"].reshape(n, -1) - out["_embed"]["points"]).abs().max() <= 2e-6
+    assert (st["distances"] - out["_embed"]["distances"]).abs().max() <= 2e-6
