@@ -7,17 +7,18 @@
 // residuals are O(2^-16) relative per product (DESIGN.md "precision of the tensor-core sample net").
 //
 // One persistent CTA per SM, one 128-ray tile at a time (UMMA M = 128, one TMEM lane per ray):
-//   warps 0-3  epilogue: thread = ray.  Encode the ray, then per layer read the accumulator from TMEM
+//   warps 0-7  epilogue (two per TMEM lane quadrant, alternating over 32-column chunks): thread = ray.  Encode the ray, then per layer read the accumulator from TMEM
 //              (tcgen05.ld 32x32b), add bias, LeakyReLU, split to bf16 hi/lo and write the next layer's A
 //              operand straight into shared memory in the UMMA K-major no-swizzle ("interleave") layout;
-//              for the last layer transpose through shared memory and store coalesced rows to HBM.
-//   warp 4     producer: streams the pre-packed weight images (one 16-wide k-step of one pass: bf16 hi and lo,
+//              for the last layer each thread stores its ray's 32 channel-major columns as one 128-byte line.
+//   warp 8     producer: streams the pre-packed weight images (one 16-wide k-step of one pass: bf16 hi and lo,
 //              already in UMMA layout) through a 4-stage ring with cp.async.bulk + mbarrier complete_tx.
-//   warp 5     MMA issuer: one lane issues tcgen05.mma / tcgen05.commit, trailing the epilogue chunk by chunk
+//   warp 9     MMA issuer: one lane issues tcgen05.mma / tcgen05.commit, trailing the epilogue chunk by chunk
 //              (a_ready barriers per 32-column chunk), with two 256-column TMEM accumulators ping-ponged
 //              across layers so layer l+1's MMAs overlap layer l's epilogue.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "hr_encode.cuh"
@@ -32,7 +33,9 @@ constexpr int NSTAGE = 4;          // weight ring depth
 constexpr int STAGE_BYTES = 16384; // one k-step image: N<=256 rows x 16 k x (hi+lo) bf16
 constexpr int CHUNK_BYTES = 8192;  // one A chunk: 128 rows x 32 k bf16
 constexpr int NCHUNK = 9;          // chunk 0 = encoded input (32, zero padded), chunks 1..8 = hidden 256
-constexpr int NTHREADS = 192;
+constexpr int EPI_GROUPS = 2;     // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
+constexpr int EPI_WARPS = 4 * EPI_GROUPS;
+constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
 constexpr int BIAS_FLOATS = 2560;
 
 // shared memory map (bytes)
@@ -80,6 +83,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -111,6 +129,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -146,9 +169,12 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
 
 }  // namespace tc
 
+// CS = cluster size: the CS CTAs of a cluster walk the weight stream in lock step; each loads 1/CS of every image
+// and multicasts it to all of them, so L2 -> SM weight traffic drops by CS.
+template <int CS>
 __global__ void __launch_bounds__(tc::NTHREADS, 1)
 mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ MlpTcPack pk, const float* __restrict__ rays,
-              float* __restrict__ heads, long long n_rays) {
+              float* __restrict__ heads, long long n_rays, int dbg_products, int dbg_load_lo) {
   using namespace tc;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -160,29 +186,36 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
   // ---- one-time setup ----
   for (int i = tid; i < pk.bias_count; i += NTHREADS) s_bias[i] = pk.bias[i];
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(BAR_FULL + s), 1); mbar_init(bar(BAR_EMPTY + s), 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(BAR_FULL + s), 1); mbar_init(bar(BAR_EMPTY + s), CS); }
     for (int c = 0; c < NCHUNK; ++c) mbar_init(bar(BAR_AREADY + c), 128);
-    for (int d = 0; d < 2; ++d) { mbar_init(bar(BAR_DFULL + d), 1); mbar_init(bar(BAR_DEMPTY + d), 128); }
+    for (int d = 0; d < 2; ++d) { mbar_init(bar(BAR_DFULL + d), 1); mbar_init(bar(BAR_DEMPTY + d), 128 * EPI_GROUPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == EPI_WARPS + 1) {
     uint32_t dst = sbase + OFF_BAR + BAR_TMEMPTR * 8;
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(dst) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can target them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
   const long long n_tiles = (n_rays + BM - 1) / BM;
   const int n_passes = pk.n_passes;
+  // every CTA of a cluster runs the same number of iterations (tiles past the end are fully masked)
+  const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
+  const long long n_clusters = gridDim.x / CS;
+  const long long cluster_id = blockIdx.x / CS;
+  const long long n_iters = (n_tiles + n_clusters * CS - 1) / (n_clusters * CS);
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     // =========================== producer: weight images, in consumption order ===========================
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (long long iter = 0; iter < n_iters; ++iter) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(pk.wpack);
         for (int p = 0; p < n_passes; ++p) {
           const uint32_t bytes = (uint32_t)pk.passes[p].n * 64u;
@@ -190,19 +223,25 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
           for (int i = 0; i < n_img; ++i, ++it) {
             const uint32_t s = it % NSTAGE;
             mbar_wait(bar(BAR_EMPTY + s), ((it / NSTAGE) & 1) ^ 1);
-            mbar_expect_tx(bar(BAR_FULL + s), bytes);
-            bulk_g2s(sbase + OFF_B + s * STAGE_BYTES, src, bytes, bar(BAR_FULL + s));
+            const uint32_t ld = dbg_load_lo ? bytes : bytes / 2;  // (diagnostic knob: skip the lo halves)
+            mbar_expect_tx(bar(BAR_FULL + s), ld);
+            if constexpr (CS == 1) {
+              bulk_g2s(sbase + OFF_B + s * STAGE_BYTES, src, ld, bar(BAR_FULL + s));
+            } else {
+              const uint32_t slice = ld / CS;
+              bulk_g2s_mc(sbase + OFF_B + s * STAGE_BYTES + crank * slice, src + crank * slice, slice, bar(BAR_FULL + s), kMask);
+            }
             src += bytes;
           }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       uint32_t it = 0, gp = 0, titer = 0;
       const int n_hidden = cfg.mlp_layers - 1;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+      for (long long iter = 0; iter < n_iters; ++iter, ++titer) {
         for (int p = 0; p < n_passes; ++p, ++gp) {
           const TcPass& P = pk.passes[p];
           const uint32_t db = gp & 1, use = gp >> 1;
@@ -228,9 +267,11 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
               const uint64_t b_lo = umma_desc(b_addr + (uint32_t)P.n * 32, (uint32_t)P.n * 16, 128);
               const uint32_t first = (ci == 0 && ks == 0) ? 0u : 1u;
               umma_bf16(d_tmem, a_hi, b_hi, idesc, first);
-              umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
-              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_commit(bar(BAR_EMPTY + s));  // frees the weight stage when these MMAs retire
+              if (dbg_products >= 2) umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+              if (dbg_products >= 3) umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+              // frees the weight stage (in every CTA of the cluster) when these MMAs retire
+              if constexpr (CS == 1) umma_commit(bar(BAR_EMPTY + s));
+              else umma_commit_mc(bar(BAR_EMPTY + s), kMask);
             }
           }
           umma_commit(bar(BAR_DFULL + db));  // accumulator complete -> epilogue
@@ -239,20 +280,17 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
     }
   } else {
     // =========================== epilogue warps: thread = ray ===========================
-    const int row = tid;  // 0..127, TMEM lane
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    // Two warps share each TMEM lane quadrant (warp w and w+4) and alternate over the 32-column chunks, so two
+    // epilogue warps are resident per scheduler and each chunk's latency chain overlaps the other group's.
+    const int grp = warp >> 2;                  // 0 or 1
+    const int row = (warp & 3) * 32 + lane;     // TMEM lane == ray within the tile
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
     uint32_t gp = 0;
-    // transpose staging: the chunk-0 slots of A_hi (warps 0,1) and A_lo (warps 2,3), 4 KB per warp; chunk 0 is only
-    // read by the first and the skip layer's MMAs, which have retired before any last-layer accumulator is full
-    float* stage_f = reinterpret_cast<float*>(smem + ((warp < 2) ? OFF_A_HI : OFF_A_LO)) + (warp & 1) * 1024;
-    bool first_tile = true;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long iter = 0; iter < n_iters; ++iter) {
+      const long long tile = (iter * n_clusters + cluster_id) * CS + crank;  // may be >= n_tiles: fully masked
       const long long ray = tile * BM + row;
-      // all four warps must be done reading the staging area (previous tile) before chunk 0 is rewritten
-      if (!first_tile) asm volatile("bar.sync 1, 128;" ::: "memory");
-      first_tile = false;
-      // ---- encode (RayParam + WindowedPE), split, write chunk 0 ----
-      {
+      // ---- encode (RayParam + WindowedPE), split, write chunk 0 (group 0 only) ----
+      if (grp == 0) {
         float enc[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) enc[i] = 0.0f;
@@ -267,6 +305,9 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
         fence_async_smem();
         mbar_arrive(bar(BAR_AREADY + 0));
       }
+      float* out_row = heads + ray * (long long)cfg.mlp_out;
+      const bool row_ok = ray < n_rays;
+      const bool vec_ok = (cfg.mlp_out & 3) == 0;
       for (int p = 0; p < n_passes; ++p, ++gp) {
         const TcPass& P = pk.passes[p];
         const uint32_t db = gp & 1, use = gp >> 1;
@@ -274,18 +315,22 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
         tc_fence_after();
         const uint32_t t_addr = tmem_base + lane_base + db * 256;
         const float* bias = s_bias + P.bias_off;
-        if (!P.is_final) {
-          for (int j = 0; j < 8; ++j) {
-            uint32_t v[32];
-            tmem_ld32(t_addr + j * 32, v);
-            if (j == 7) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+        const int nchunks = P.is_final ? (P.n + 31) / 32 : 8;
+        // this group's last chunk; a group with no chunk in this pass releases the accumulator right away
+        const int last_j = (grp < nchunks) ? ((nchunks - 1 - grp) / EPI_GROUPS) * EPI_GROUPS + grp : -1;
+        if (last_j < 0) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+        for (int j = grp; j < nchunks; j += EPI_GROUPS) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + j * 32, v);
+          if (j == last_j) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+          if (!P.is_final) {
 #pragma unroll
             for (int kg = 0; kg < 4; ++kg) {
               float x[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 float t = __uint_as_float(v[kg * 8 + i]) + bias[j * 32 + kg * 8 + i];
-                x[i] = (t > 0.0f) ? t : t * cfg.leaky_slope;
+                x[i] = fmaxf(t, t * cfg.leaky_slope);  // LeakyReLU, slope in (0,1)
               }
               uint4 hi, lo;
               split8(x, hi, lo);
@@ -295,25 +340,29 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
             }
             fence_async_smem();
             mbar_arrive(bar(BAR_AREADY + 1 + j));
-          }
-        } else {
-          const int nchunks = (P.n + 31) / 32;
-          for (int j = 0; j < nchunks; ++j) {
-            uint32_t v[32];
-            tmem_ld32(t_addr + j * 32, v);
-            if (j == nchunks - 1) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
-            // transpose through shared memory (XOR swizzle, conflict free) -> coalesced row stores
+          } else {
+            // last layer: this thread owns 32 consecutive channel-major columns of its ray = one 128-byte line
+            const int c0 = P.out_col0 + j * 32;
+            const int nvalid = min(min(32, P.n - j * 32), cfg.mlp_out - c0);
+            if (row_ok && nvalid > 0) {
+              if (vec_ok) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) stage_f[lane * 32 + (i ^ lane)] = __uint_as_float(v[i]) + bias[j * 32 + i];
-            __syncwarp();
-            const int col = P.out_col0 + j * 32 + lane;
-            const bool col_ok = (j * 32 + lane < P.n) && (col < cfg.mlp_out);
-            for (int rr = 0; rr < 32; ++rr) {
-              const long long r = tile * BM + warp * 32 + rr;
-              float o = stage_f[rr * 32 + (lane ^ rr)];
-              if (col_ok && r < n_rays) heads[r * cfg.mlp_out + col] = o;
+                for (int i4 = 0; i4 < 8; ++i4) {
+                  if (i4 * 4 < nvalid) {
+                    float4 o;
+                    o.x = __uint_as_float(v[i4 * 4 + 0]) + bias[j * 32 + i4 * 4 + 0];
+                    o.y = __uint_as_float(v[i4 * 4 + 1]) + bias[j * 32 + i4 * 4 + 1];
+                    o.z = __uint_as_float(v[i4 * 4 + 2]) + bias[j * 32 + i4 * 4 + 2];
+                    o.w = __uint_as_float(v[i4 * 4 + 3]) + bias[j * 32 + i4 * 4 + 3];
+                    *reinterpret_cast<float4*>(out_row + c0 + i4 * 4) = o;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < nvalid) out_row[c0 + i] = __uint_as_float(v[i]) + bias[j * 32 + i];
+              }
             }
-            __syncwarp();
           }
         }
       }
@@ -323,7 +372,8 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if constexpr (CS > 1) cluster_sync_all();  // no CTA leaves while a peer can still signal its barriers
+  if (warp == EPI_WARPS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
@@ -439,15 +489,40 @@ int pack_mlp_tc(hr_handle* h, const hr_params*, const float* const* w_dev, const
   return 0;
 }
 
+template <int CS>
+static cudaError_t launch_mlp_tc_cs(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
+                                    int num_sms, cudaStream_t stream, int dbg_products, int dbg_load_lo) {
+  long long tiles = (n + tc::BM - 1) / tc::BM;
+  long long want = (tiles + CS - 1) / CS * CS;
+  long long cap = (long long)(num_sms / CS) * CS;
+  int grid = (int)(want < cap ? want : cap);
+  if (grid < CS) grid = CS;
+  cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(tc::NTHREADS);
+  lc.dynamicSmemBytes = tc::SMEM_BYTES;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, mlp_tc_kernel<CS>, cfg, pk, rays, heads, n, dbg_products, dbg_load_lo);
+}
+
 cudaError_t launch_mlp_tc(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
                           int num_sms, cudaStream_t stream) {
-  long long tiles = (n + tc::BM - 1) / tc::BM;
-  int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  if (grid < 1) grid = 1;
-  cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  mlp_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, stream>>>(cfg, pk, rays, heads, n);
-  return cudaGetLastError();
+  // diagnostic knobs (profiling only; defaults = the product path)
+  static const int dbg_products = getenv("HR_TC_PRODUCTS") ? atoi(getenv("HR_TC_PRODUCTS")) : 3;
+  static const int dbg_load_lo = getenv("HR_TC_LOAD_LO") ? atoi(getenv("HR_TC_LOAD_LO")) : 1;
+  static const int cluster = getenv("HR_TC_CLUSTER") ? atoi(getenv("HR_TC_CLUSTER")) : 2;
+  if (cluster == 4) return launch_mlp_tc_cs<4>(cfg, pk, rays, heads, n, num_sms, stream, dbg_products, dbg_load_lo);
+  if (cluster == 2) return launch_mlp_tc_cs<2>(cfg, pk, rays, heads, n, num_sms, stream, dbg_products, dbg_load_lo);
+  return launch_mlp_tc_cs<1>(cfg, pk, rays, heads, n, num_sms, stream, dbg_products, dbg_load_lo);
 }
 
 }  // namespace hr
