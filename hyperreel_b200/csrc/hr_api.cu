@@ -63,6 +63,29 @@ __global__ void pack_channel_last(const float* __restrict__ src, float* __restri
   }
 }
 
+// (axis, time) planes -> per-keyframe lines.  The reference samples plane_time[1,C,K,L] bilinearly at (u_c, tau) where
+// tau = normalize_time_coord(base_t) (tensorf_dynamic.py:615-616) and base_t is the ray's keyframe time
+// (utils/flow_utils.py:18-31): tau therefore takes exactly K values, one per keyframe k, and the two rows grid_sample
+// blends (rows it_k, it_k+1 with fraction ft_k, align_corners=True) are a property of k alone.  dst[k][l][c] holds that
+// blend, so the render kernel's second factor is a 2-tap linear lookup instead of 4 taps.
+__global__ void pack_time_lines(const float* __restrict__ src, float* __restrict__ dst, int C, int K, int L, float inv_fac,
+                                float time_scale, float time_offset) {
+  long long total = (long long)K * L * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int l = (int)((i / C) % L);
+    int k = (int)(i / ((long long)C * L));
+    float base_t = __fmul_rn((float)k, inv_fac);
+    float tau = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(base_t, time_scale), time_offset), 2.0f), 1.0f);
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(tau, 1.0f), 0.5f), (float)(K - 1));
+    int it = max(0, min((int)floorf(iy), K - 2));
+    float ft = iy - (float)it;
+    float a = src[((long long)c * K + it) * L + l];
+    float b = src[((long long)c * K + it + 1) * L + l];
+    dst[i] = __fmul_rn(1.0f - ft, a) + __fmul_rn(ft, b);
+  }
+}
+
 // Wt[k][n] (k-major, zero padded) from the reference weight W[out][in] (nn.Linear layout).
 //   k -> source column: k < in_pad: (k < in_ch ? k : none) when the layer consumes the encoded input;
 //                        hidden rows follow.  n -> source row: last layer channel-major permutation.
@@ -295,9 +318,25 @@ int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
     if (C > 0 && (ts.H < 2 || ts.W < 2 || ts.L < 2)) { rc = fail("hr_upload: plane %d too small (%dx%d, L=%d)", i, ts.H, ts.W, ts.L); break; }
     if ((rc = pack_tab(p->sigma_plane[i], C, ts.H, ts.W, &ts.space))) break;
     if ((rc = pack_tab(p->app_plane[i], C, ts.H, ts.W, &ta.space))) break;
-    // second factor: dynamic [C][K][L] -> [K][L][C]; static [C][L][1] -> [1][L][C]
-    if ((rc = pack_tab(p->sigma_second[i], C, H2, ts.L, &ts.second))) break;
-    if ((rc = pack_tab(p->app_second[i], C, H2, ts.L, &ta.second))) break;
+    // second factor: static [C][L][1] -> [1][L][C]; dynamic [C][K][L] -> K pre-blended keyframe lines [K][L][C]
+    if (!c.dynamic) {
+      if ((rc = pack_tab(p->sigma_second[i], C, H2, ts.L, &ts.second))) break;
+      if ((rc = pack_tab(p->app_second[i], C, H2, ts.L, &ta.second))) break;
+    } else if (C > 0) {
+      if (H2 < 2) { rc = fail("hr_upload: the keyframe (time) planes need at least 2 keyframes"); break; }
+      for (int f = 0; f < 2 && !rc; ++f) {
+        const float* srcp = f ? p->app_second[i] : p->sigma_second[i];
+        if (!srcp) { rc = fail("hr_upload: time plane %d missing", i); break; }
+        const float* d = nullptr;
+        if ((rc = stage_in(srcp, (size_t)C * H2 * ts.L, p->on_device, st, temps, &d))) break;
+        float* dst = nullptr;
+        if ((rc = dev_alloc(h, (void**)&dst, (size_t)C * H2 * ts.L * sizeof(float)))) break;
+        pack_time_lines<<<grid_for((long long)C * H2 * ts.L), 256, 0, st>>>(d, dst, C, H2, ts.L, h->dv.time_inv_fac,
+                                                                            h->dv.time_scale, h->dv.time_offset);
+        (f ? ta.second : ts.second) = dst;
+      }
+      if (rc) break;
+    }
   }
   if (!rc) {
     // every table derives from one gridSize (tensorf_base.py:911-944, tensorf_dynamic.py:126-169): plane i is

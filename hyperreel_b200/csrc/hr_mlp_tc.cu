@@ -7,17 +7,18 @@
 // residuals are O(2^-16) relative per product (DESIGN.md "precision of the tensor-core sample net").
 //
 // One persistent CTA per SM, one 128-ray tile at a time (UMMA M = 128, one TMEM lane per ray):
-//   warps 0-7  epilogue (two per TMEM lane quadrant, alternating over 32-column chunks): thread = ray.  Encode the ray, then per layer read the accumulator from TMEM
+//   warps 0-15 epilogue (four per TMEM lane quadrant, alternating over 32-column chunks): thread = ray.  Encode the ray, then per layer read the accumulator from TMEM
 //              (tcgen05.ld 32x32b), add bias, LeakyReLU, split to bf16 hi/lo and write the next layer's A
 //              operand straight into shared memory in the UMMA K-major no-swizzle ("interleave") layout;
 //              for the last layer each thread stores its ray's 32 channel-major columns as one 128-byte line.
-//   warp 8     producer: streams the pre-packed weight images (one 16-wide k-step of one pass: bf16 hi and lo,
+//   warp 16    producer: streams the pre-packed weight images (one 16-wide k-step of one pass: bf16 hi and lo,
 //              already in UMMA layout) through a 4-stage ring with cp.async.bulk + mbarrier complete_tx.
-//   warp 9     MMA issuer: one lane issues tcgen05.mma / tcgen05.commit, trailing the epilogue chunk by chunk
+//   warp 17    MMA issuer: one lane issues tcgen05.mma / tcgen05.commit, trailing the epilogue chunk by chunk
 //              (a_ready barriers per 32-column chunk), with two 256-column TMEM accumulators ping-ponged
 //              across layers so layer l+1's MMAs overlap layer l's epilogue.
 #include <cuda_bf16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -33,7 +34,7 @@ constexpr int NSTAGE = 4;          // weight ring depth
 constexpr int STAGE_BYTES = 16384; // one k-step image: N<=256 rows x 16 k x (hi+lo) bf16
 constexpr int CHUNK_BYTES = 8192;  // one A chunk: 128 rows x 32 k bf16
 constexpr int NCHUNK = 9;          // chunk 0 = encoded input (32, zero padded), chunks 1..8 = hidden 256
-constexpr int EPI_GROUPS = 2;     // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
+constexpr int EPI_GROUPS = 4;     // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
 constexpr int EPI_WARPS = 4 * EPI_GROUPS;
 constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
 constexpr int BIAS_FLOATS = 2560;
@@ -174,7 +175,7 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
 template <int CS>
 __global__ void __launch_bounds__(tc::NTHREADS, 1)
 mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ MlpTcPack pk, const float* __restrict__ rays,
-              float* __restrict__ heads, long long n_rays, int dbg_products, int dbg_load_lo) {
+              float* __restrict__ heads, long long n_rays, int dbg_products, int dbg_load_lo, unsigned long long* trace) {
   using namespace tc;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -204,6 +205,11 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
 
   const long long n_tiles = (n_rays + BM - 1) / BM;
   const int n_passes = pk.n_passes;
+  // diagnostic timeline (HR_TC_TRACE): CTA 0, second tile; slot = (pass * 8 + event)
+  const bool tracing = (trace != nullptr) && (blockIdx.x == 0);
+  auto TR = [&](long long iter, int pass, int ev) {
+    if (tracing && iter == 1) trace[pass * 8 + ev] = clock64();
+  };
   // every CTA of a cluster runs the same number of iterations (tiles past the end are fully masked)
   const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
   const long long n_clusters = gridDim.x / CS;
@@ -248,12 +254,15 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
           const uint32_t d_tmem = tmem_base + db * 256;
           const uint32_t idesc = umma_idesc(P.n);
           mbar_wait(bar(BAR_DEMPTY + db), (use & 1) ^ 1);  // accumulator drained by its previous reader
+          TR(iter, p, 0);
           for (int ci = 0; ci < P.n_chunks; ++ci) {
             const int c = P.first_chunk + ci;
             if (P.wait_a) {
               // chunk 0: written once per tile by the encoder; chunks 1..8: once per hidden layer
               const uint32_t done = (c == 0) ? titer : (titer * n_hidden + (uint32_t)(P.layer - 1));
               mbar_wait(bar(BAR_AREADY + c), done & 1);
+              if (ci == 0) TR(iter, p, 1);
+              if (ci == P.n_chunks - 1) TR(iter, p, 2);
             }
             for (int ks = 0; ks < 2; ++ks, ++it) {
               const uint32_t s = it % NSTAGE;
@@ -275,6 +284,7 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
             }
           }
           umma_commit(bar(BAR_DFULL + db));  // accumulator complete -> epilogue
+          TR(iter, p, 3);
         }
       }
     }
@@ -282,7 +292,7 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
     // =========================== epilogue warps: thread = ray ===========================
     // Two warps share each TMEM lane quadrant (warp w and w+4) and alternate over the 32-column chunks, so two
     // epilogue warps are resident per scheduler and each chunk's latency chain overlaps the other group's.
-    const int grp = warp >> 2;                  // 0 or 1
+    const int grp = warp >> 2;                  // 0 .. EPI_GROUPS-1
     const int row = (warp & 3) * 32 + lane;     // TMEM lane == ray within the tile
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
     uint32_t gp = 0;
@@ -312,6 +322,7 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
         const TcPass& P = pk.passes[p];
         const uint32_t db = gp & 1, use = gp >> 1;
         mbar_wait(bar(BAR_DFULL + db), use & 1);
+        if (tid == 0) TR(iter, p, 4);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + lane_base + db * 256;
         const float* bias = s_bias + P.bias_off;
@@ -323,13 +334,25 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
           uint32_t v[32];
           tmem_ld32(t_addr + j * 32, v);
           if (j == last_j) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+          // bias of these 32 columns (shared-memory broadcast, 16-byte loads), folded into v
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + j * 32);
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 b = b4[i4];
+              v[i4 * 4 + 0] = __float_as_uint(__uint_as_float(v[i4 * 4 + 0]) + b.x);
+              v[i4 * 4 + 1] = __float_as_uint(__uint_as_float(v[i4 * 4 + 1]) + b.y);
+              v[i4 * 4 + 2] = __float_as_uint(__uint_as_float(v[i4 * 4 + 2]) + b.z);
+              v[i4 * 4 + 3] = __float_as_uint(__uint_as_float(v[i4 * 4 + 3]) + b.w);
+            }
+          }
           if (!P.is_final) {
 #pragma unroll
             for (int kg = 0; kg < 4; ++kg) {
               float x[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                float t = __uint_as_float(v[kg * 8 + i]) + bias[j * 32 + kg * 8 + i];
+                const float t = __uint_as_float(v[kg * 8 + i]);
                 x[i] = fmaxf(t, t * cfg.leaky_slope);  // LeakyReLU, slope in (0,1)
               }
               uint4 hi, lo;
@@ -340,6 +363,8 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
             }
             fence_async_smem();
             mbar_arrive(bar(BAR_AREADY + 1 + j));
+            if (tid == 0 && j == 0) TR(iter, p, 5);
+            if (lane == 0 && (warp & 3) == 0 && j == 7) TR(iter, p, 6);
           } else {
             // last layer: this thread owns 32 consecutive channel-major columns of its ray = one 128-byte line
             const int c0 = P.out_col0 + j * 32;
@@ -350,17 +375,17 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
                 for (int i4 = 0; i4 < 8; ++i4) {
                   if (i4 * 4 < nvalid) {
                     float4 o;
-                    o.x = __uint_as_float(v[i4 * 4 + 0]) + bias[j * 32 + i4 * 4 + 0];
-                    o.y = __uint_as_float(v[i4 * 4 + 1]) + bias[j * 32 + i4 * 4 + 1];
-                    o.z = __uint_as_float(v[i4 * 4 + 2]) + bias[j * 32 + i4 * 4 + 2];
-                    o.w = __uint_as_float(v[i4 * 4 + 3]) + bias[j * 32 + i4 * 4 + 3];
+                    o.x = __uint_as_float(v[i4 * 4 + 0]);
+                    o.y = __uint_as_float(v[i4 * 4 + 1]);
+                    o.z = __uint_as_float(v[i4 * 4 + 2]);
+                    o.w = __uint_as_float(v[i4 * 4 + 3]);
                     *reinterpret_cast<float4*>(out_row + c0 + i4 * 4) = o;
                   }
                 }
               } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                  if (i < nvalid) out_row[c0 + i] = __uint_as_float(v[i]) + bias[j * 32 + i];
+                  if (i < nvalid) out_row[c0 + i] = __uint_as_float(v[i]);
               }
             }
           }
@@ -492,6 +517,12 @@ int pack_mlp_tc(hr_handle* h, const hr_params*, const float* const* w_dev, const
 template <int CS>
 static cudaError_t launch_mlp_tc_cs(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
                                     int num_sms, cudaStream_t stream, int dbg_products, int dbg_load_lo) {
+  unsigned long long* trace = nullptr;
+  const bool want_trace = getenv("HR_TC_TRACE") != nullptr;
+  if (want_trace) {
+    cudaMalloc((void**)&trace, 16 * 8 * sizeof(unsigned long long));
+    cudaMemset(trace, 0, 16 * 8 * sizeof(unsigned long long));
+  }
   long long tiles = (n + tc::BM - 1) / tc::BM;
   long long want = (tiles + CS - 1) / CS * CS;
   long long cap = (long long)(num_sms / CS) * CS;
@@ -511,7 +542,21 @@ static cudaError_t launch_mlp_tc_cs(const hr_config& cfg, const MlpTcPack& pk, c
   at[0].val.clusterDim.z = 1;
   lc.attrs = at;
   lc.numAttrs = 1;
-  return cudaLaunchKernelEx(&lc, mlp_tc_kernel<CS>, cfg, pk, rays, heads, n, dbg_products, dbg_load_lo);
+  cudaError_t le = cudaLaunchKernelEx(&lc, mlp_tc_kernel<CS>, cfg, pk, rays, heads, n, dbg_products, dbg_load_lo, trace);
+  if (want_trace) {
+    unsigned long long h[16 * 8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(trace);
+    unsigned long long t0 = h[0];
+    fprintf(stderr, "[tc-trace] pass: demp_ok a_first a_last commit | dfull_seen first_chunk last_chunk (cycles rel. to pass 0)\n");
+    for (int p = 0; p < pk.n_passes; ++p) {
+      fprintf(stderr, "[tc-trace] %2d:", p);
+      for (int e = 0; e < 7; ++e) fprintf(stderr, " %8lld", h[p * 8 + e] ? (long long)(h[p * 8 + e] - t0) : -1LL);
+      fprintf(stderr, "\n");
+    }
+  }
+  return le;
 }
 
 cudaError_t launch_mlp_tc(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,

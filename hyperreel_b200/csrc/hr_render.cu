@@ -137,43 +137,44 @@ __device__ __forceinline__ void interp(const Taps<C, ROWS2>& t, float w0, float 
 
 // One VM group (space plane x second factor) of one field for one sample.
 //   ia/fa, ib/fb : texel index / fraction along the plane's x and y axes; ic/fc along the second factor's axis
-//   it/ft        : keyframe row / fraction (dynamic) -- per-ray constants
+//   krow         : row of the second-factor table: the ray's keyframe (dynamic; hr_upload pre-blends the two
+//                  keyframe rows grid_sample would mix for that keyframe, see pack_time_lines) or 0 (static line)
 template <int C, bool DYN>
 struct GroupTaps {
   Taps<C, true> sp;
-  Taps<C, DYN> se;
+  Taps<C, false> se;
 };
 
 template <int C, bool DYN>
-__device__ __forceinline__ void group_fetch(GroupTaps<C, DYN>& g, const PlaneTab& T, int ia, int ib, int ic, int it, int xt,
+__device__ __forceinline__ void group_fetch(GroupTaps<C, DYN>& g, const PlaneTab& T, int ia, int ib, int ic, int krow, int xt,
                                             int alt, bool ok) {
   int so, eo;
   if constexpr (C == 8) {
     so = ((ib * T.W + ia + xt) << 3) + (alt << 2);
-    eo = ((it * T.L + ic + xt) << 3) + (alt << 2);
+    eo = ((krow * T.L + ic + xt) << 3) + (alt << 2);
   } else {
     so = ((ib + alt) * T.W + ia + xt) << 2;
-    eo = ((DYN ? (it + alt) : 0) * T.L + ic + xt) << 2;
+    eo = (krow * T.L + ic + xt) << 2;
   }
   so = ok ? so : 0;
   eo = ok ? eo : 0;
   fetch<C, true>(g.sp, T.space, so, T.W * C);
-  fetch<C, DYN>(g.se, T.second, eo, T.L * C);
+  fetch<C, false>(g.se, T.second, eo, 0);
 }
 
 // -> prod[4] = space_c * second_c for this lane's channels (C==8: own half; C==4: all, replicated)
 template <int C, bool DYN>
-__device__ __forceinline__ void group_products(const GroupTaps<C, DYN>& g, float fa, float fb, float fc, float ft, int xt,
-                                               int alt, float (&prod)[4]) {
+__device__ __forceinline__ void group_products(const GroupTaps<C, DYN>& g, float fa, float fb, float fc, int xt, int alt,
+                                               float (&prod)[4]) {
   const float wa = xt ? fa : 1.0f - fa;
   const float wc = xt ? fc : 1.0f - fc;
   float A[4], B[4];
   if constexpr (C == 8) {
     interp<C, true>(g.sp, wa * (1.0f - fb), wa * fb, A);
-    interp<C, DYN>(g.se, DYN ? wc * (1.0f - ft) : wc, wc * ft, B);
+    interp<C, false>(g.se, wc, 0.0f, B);
   } else {
     interp<C, true>(g.sp, wa * (alt ? fb : 1.0f - fb), 0.0f, A);
-    interp<C, DYN>(g.se, wc * (DYN ? (alt ? ft : 1.0f - ft) : (alt ? 0.0f : 1.0f)), 0.0f, B);
+    interp<C, false>(g.se, alt ? 0.0f : wc, 0.0f, B);
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) prod[c] = A[c] * B[c];
@@ -260,21 +261,15 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     }
 
     // ---- per-ray keyframe snap (utils/flow_utils.py:18-31), time coordinate and keyframe row ----
-    float toff = 0.0f, ft = 0.0f;
-    int it = 0;
+    float toff = 0.0f;
+    int krow = 0;  // keyframe index: the time coordinate of every sample of this ray depends only on it
     if (DYN || cfg.use_flow) {
       float tt = __fmul_rn(time, dv.time_fac);
       tt = fminf(fmaxf(tt, 0.0f), dv.kf_max);
       tt = rintf(__fsub_rn(tt, 1e-5f));
       const float base_t = __fmul_rn(tt, dv.time_inv_fac);
       toff = __fsub_rn(time, base_t);
-      if (DYN) {
-        // normalize_time_coord (tensorf_dynamic.py:615-616) then grid_sample's unnormalise over K rows
-        const float tau = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(base_t, dv.time_scale), dv.time_offset), 2.0f), 1.0f);
-        const float iy = __fmul_rn(__fmul_rn(__fadd_rn(tau, 1.0f), 0.5f), (float)(dv.kt - 1));
-        it = max(0, min((int)floorf(iy), dv.kt - 2));
-        ft = iy - (float)it;
-      }
+      if (DYN) krow = max(0, min((int)tt, dv.kt - 1));
     }
 
     // ---- view-dependent appearance matrix: G[q][i] = sum_k Y_k(dir) * basis[(q*9+k)][i]  (tensorf_utils.py:334-338)
@@ -443,25 +438,25 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       GroupTaps<C0, DYN> s0, a0;
       GroupTaps<(C1 ? C1 : 4), DYN> s1, a1;
       GroupTaps<(C2 ? C2 : 4), DYN> s2, a2;
-      group_fetch<C0, DYN>(s0, tabs.sig[0], sx, sy, sz, it, xt, alt, ok);
-      group_fetch<C0, DYN>(a0, tabs.app[0], sx, sy, sz, it, xt, alt, ok);
+      group_fetch<C0, DYN>(s0, tabs.sig[0], sx, sy, sz, krow, xt, alt, ok);
+      group_fetch<C0, DYN>(a0, tabs.app[0], sx, sy, sz, krow, xt, alt, ok);
       if constexpr (C1 > 0) {
-        group_fetch<C1, DYN>(s1, tabs.sig[1], sx, sz, sy, it, xt, alt, ok);
-        group_fetch<C1, DYN>(a1, tabs.app[1], sx, sz, sy, it, xt, alt, ok);
+        group_fetch<C1, DYN>(s1, tabs.sig[1], sx, sz, sy, krow, xt, alt, ok);
+        group_fetch<C1, DYN>(a1, tabs.app[1], sx, sz, sy, krow, xt, alt, ok);
       }
       if constexpr (C2 > 0) {
-        group_fetch<C2, DYN>(s2, tabs.sig[2], sy, sz, sx, it, xt, alt, ok);
-        group_fetch<C2, DYN>(a2, tabs.app[2], sy, sz, sx, it, xt, alt, ok);
+        group_fetch<C2, DYN>(s2, tabs.sig[2], sy, sz, sx, krow, xt, alt, ok);
+        group_fetch<C2, DYN>(a2, tabs.app[2], sy, sz, sx, krow, xt, alt, ok);
       }
       // density feature: sum_c space_c * second_c over all groups (tensorf_dynamic.py:330, tensorf_no_sample.py:76-78)
       float f[NT];
       float sf;
       {
         float p[4];
-        group_products<C0, DYN>(s0, gx, gy, gz, ft, xt, alt, p);
+        group_products<C0, DYN>(s0, gx, gy, gz, xt, alt, p);
         sf = (p[0] + p[1]) + (p[2] + p[3]);
         if constexpr (C0 == 8) sf += __shfl_xor_sync(kFull, sf, 1);
-        group_products<C0, DYN>(a0, gx, gy, gz, ft, xt, alt, p);
+        group_products<C0, DYN>(a0, gx, gy, gz, xt, alt, p);
 #pragma unroll
         for (int c = 0; c < 4; ++c) f[c] = p[c];
         if constexpr (C0 == 8) {
@@ -471,11 +466,11 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       }
       if constexpr (C1 > 0) {
         float p[4];
-        group_products<C1, DYN>(s1, gx, gz, gy, ft, xt, alt, p);
+        group_products<C1, DYN>(s1, gx, gz, gy, xt, alt, p);
         float part = (p[0] + p[1]) + (p[2] + p[3]);
         if constexpr (C1 == 8) part += __shfl_xor_sync(kFull, part, 1);
         sf += part;
-        group_products<C1, DYN>(a1, gx, gz, gy, ft, xt, alt, p);
+        group_products<C1, DYN>(a1, gx, gz, gy, xt, alt, p);
 #pragma unroll
         for (int c = 0; c < 4; ++c) f[C0 + c] = p[c];
         if constexpr (C1 == 8) {
@@ -485,11 +480,11 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       }
       if constexpr (C2 > 0) {
         float p[4];
-        group_products<C2, DYN>(s2, gy, gz, gx, ft, xt, alt, p);
+        group_products<C2, DYN>(s2, gy, gz, gx, xt, alt, p);
         float part = (p[0] + p[1]) + (p[2] + p[3]);
         if constexpr (C2 == 8) part += __shfl_xor_sync(kFull, part, 1);
         sf += part;
-        group_products<C2, DYN>(a2, gy, gz, gx, ft, xt, alt, p);
+        group_products<C2, DYN>(a2, gy, gz, gx, xt, alt, p);
 #pragma unroll
         for (int c = 0; c < 4; ++c) f[C0 + C1 + c] = p[c];
         if constexpr (C2 == 8) {
