@@ -266,7 +266,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mlp", default=os.environ.get("HR_BENCH_MLP", "fp32"), choices=["fp32", "bf16x3"])
+    ap.add_argument("--mlp", default=os.environ.get("HR_BENCH_MLP", "bf16x3"), choices=["fp32", "bf16x3"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -10,7 +10,8 @@
 //   warps 0-15 epilogue (four per TMEM lane quadrant, alternating over 32-column chunks): thread = ray.  Encode the ray, then per layer read the accumulator from TMEM
 //              (tcgen05.ld 32x32b), add bias, LeakyReLU, split to bf16 hi/lo and write the next layer's A
 //              operand straight into shared memory in the UMMA K-major no-swizzle ("interleave") layout;
-//              for the last layer each thread stores its ray's 32 channel-major columns as one 128-byte line.
+//              The last layer is computed transposed (weights as the A operand): lane = output column, so each
+//              warp stores one coalesced 128-byte line per ray and the bias is a single register.
 //   warp 16    producer: streams the pre-packed weight images (one 16-wide k-step of one pass: bf16 hi and lo,
 //              already in UMMA layout) through a 4-stage ring with cp.async.bulk + mbarrier complete_tx.
 //   warp 17    MMA issuer: one lane issues tcgen05.mma / tcgen05.commit, trailing the epilogue chunk by chunk
@@ -34,7 +35,7 @@ constexpr int NSTAGE = 4;          // weight ring depth
 constexpr int STAGE_BYTES = 16384; // one k-step image: N<=256 rows x 16 k x (hi+lo) bf16
 constexpr int CHUNK_BYTES = 8192;  // one A chunk: 128 rows x 32 k bf16
 constexpr int NCHUNK = 9;          // chunk 0 = encoded input (32, zero padded), chunks 1..8 = hidden 256
-constexpr int EPI_GROUPS = 4;     // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
+constexpr int EPI_GROUPS = 2;     // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
 constexpr int EPI_WARPS = 4 * EPI_GROUPS;
 constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
 constexpr int BIAS_FLOATS = 2560;
@@ -45,7 +46,8 @@ constexpr int OFF_A_LO = OFF_A_HI + NCHUNK * CHUNK_BYTES;   // 73728
 constexpr int OFF_B = OFF_A_LO + NCHUNK * CHUNK_BYTES;      // 147456
 constexpr int OFF_BIAS = OFF_B + NSTAGE * STAGE_BYTES;      // 212992
 constexpr int OFF_BAR = OFF_BIAS + BIAS_FLOATS * 4;         // 223232
-constexpr int SMEM_BYTES = OFF_BAR + 256;                   // 223488
+constexpr int OFF_STG = OFF_BAR + 256;                      // 223488: last-layer transpose staging, 1 KB per epilogue warp
+constexpr int SMEM_BYTES = OFF_STG + EPI_WARPS * 1024;      // 231680 (of 232448 available)
 
 // barrier slots (8 bytes each) inside OFF_BAR
 constexpr int BAR_FULL = 0;                 // [NSTAGE]
@@ -150,6 +152,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // Offset (bytes) of the 16-byte row slot holding k-group kg of row `row` inside a 128-row x 32-k chunk.
 __device__ __forceinline__ uint32_t a_slot(int row, int kg) { return (uint32_t)((kg * 16 + (row >> 3)) * 128 + (row & 7) * 16); }
 
@@ -188,7 +208,8 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
   for (int i = tid; i < pk.bias_count; i += NTHREADS) s_bias[i] = pk.bias[i];
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(BAR_FULL + s), 1); mbar_init(bar(BAR_EMPTY + s), CS); }
-    for (int c = 0; c < NCHUNK; ++c) mbar_init(bar(BAR_AREADY + c), 128);
+    mbar_init(bar(BAR_AREADY + 0), 128);  // chunk 0: the encoder (group 0)
+    for (int c = 1; c < NCHUNK; ++c) mbar_init(bar(BAR_AREADY + c), 128 * EPI_GROUPS);  // every group writes a slice
     for (int d = 0; d < 2; ++d) { mbar_init(bar(BAR_DFULL + d), 1); mbar_init(bar(BAR_DEMPTY + d), 128 * EPI_GROUPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -244,17 +265,26 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
     }
   } else if (warp == EPI_WARPS + 1) {
     // =========================== MMA issuer ===========================
+    // One thread feeds the tensor core, so its own instruction stream is on the critical path: descriptors are
+    // built once and advanced with adds, stage/phase are kept incrementally, and the three split products plus the
+    // stage-release commit of a k-step go out in a single asm block.
     if (lane == 0) {
-      uint32_t it = 0, gp = 0, titer = 0;
+      uint32_t stage = 0, phase = 0, gp = 0, titer = 0;
       const int n_hidden = cfg.mlp_layers - 1;
+      // descriptor of the first activation k-step / first weight stage; later ones differ only in the start address
+      const uint64_t hdesc_hi0 = umma_desc(sbase + OFF_A_HI, 2048, 128);
+      const uint64_t hdesc_lo0 = umma_desc(sbase + OFF_A_LO, 2048, 128);
       for (long long iter = 0; iter < n_iters; ++iter, ++titer) {
         for (int p = 0; p < n_passes; ++p, ++gp) {
           const TcPass& P = pk.passes[p];
           const uint32_t db = gp & 1, use = gp >> 1;
           const uint32_t d_tmem = tmem_base + db * 256;
           const uint32_t idesc = umma_idesc(P.n);
+          const uint64_t wdesc_hi0 = umma_desc(sbase + OFF_B, (uint32_t)P.n * 16, 128);
+          const uint64_t wdesc_lo0 = umma_desc(sbase + OFF_B + (uint32_t)P.n * 32, (uint32_t)P.n * 16, 128);
           mbar_wait(bar(BAR_DEMPTY + db), (use & 1) ^ 1);  // accumulator drained by its previous reader
           TR(iter, p, 0);
+          uint32_t acc = 0;
           for (int ci = 0; ci < P.n_chunks; ++ci) {
             const int c = P.first_chunk + ci;
             if (P.wait_a) {
@@ -264,23 +294,61 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
               if (ci == 0) TR(iter, p, 1);
               if (ci == P.n_chunks - 1) TR(iter, p, 2);
             }
-            for (int ks = 0; ks < 2; ++ks, ++it) {
-              const uint32_t s = it % NSTAGE;
-              mbar_wait(bar(BAR_FULL + s), (it / NSTAGE) & 1);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const int kidx = ci * 2 + ks;
+              const bool ktr = tracing && iter == 1 && (p == 2 || p == 6) && kidx < 16;
+              const int kbase = 128 + (p == 6 ? 64 : 0) + kidx * 4;
+              if (ktr) trace[kbase + 0] = clock64();
+              mbar_wait(bar(BAR_FULL + stage), phase);
+              if (ktr) trace[kbase + 1] = clock64();
               tc_fence_after();
-              const uint32_t a_off = c * CHUNK_BYTES + ks * 4096;
-              const uint64_t a_hi = umma_desc(sbase + OFF_A_HI + a_off, 2048, 128);
-              const uint64_t a_lo = umma_desc(sbase + OFF_A_LO + a_off, 2048, 128);
-              const uint32_t b_addr = sbase + OFF_B + s * STAGE_BYTES;
-              const uint64_t b_hi = umma_desc(b_addr, (uint32_t)P.n * 16, 128);
-              const uint64_t b_lo = umma_desc(b_addr + (uint32_t)P.n * 32, (uint32_t)P.n * 16, 128);
-              const uint32_t first = (ci == 0 && ks == 0) ? 0u : 1u;
-              umma_bf16(d_tmem, a_hi, b_hi, idesc, first);
-              if (dbg_products >= 2) umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
-              if (dbg_products >= 3) umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-              // frees the weight stage (in every CTA of the cluster) when these MMAs retire
-              if constexpr (CS == 1) umma_commit(bar(BAR_EMPTY + s));
-              else umma_commit_mc(bar(BAR_EMPTY + s), kMask);
+              const uint64_t hoff = (uint64_t)((c * CHUNK_BYTES + ks * 4096) >> 4);
+              const uint64_t woff = (uint64_t)((stage * STAGE_BYTES) >> 4);
+              const uint64_t h_hi = hdesc_hi0 + hoff, h_lo = hdesc_lo0 + hoff;  // activations, 128 rays x 16 k
+              const uint64_t w_hi = wdesc_hi0 + woff, w_lo = wdesc_lo0 + woff;  // weights, P.n rows x 16 k
+              // D[ray, col] += H * W^T : A = activations (M = 128 rays), B = weights (N = P.n columns)
+              const uint64_t a0 = h_hi, b0 = w_hi;  // hi * hi
+              const uint64_t a1 = h_lo, b1 = w_hi;  // (act lo) * (weight hi)
+              const uint64_t a2 = h_hi, b2 = w_lo;  // (act hi) * (weight lo)
+              const uint32_t ebar = bar(BAR_EMPTY + stage);
+              if (dbg_products >= 3) {
+                if constexpr (CS == 1) {
+                  asm volatile(
+                      "{\n\t"
+                      ".reg .pred p, q;\n\t"
+                      "setp.ne.b32 p, %8, 0;\n\t"
+                      "setp.eq.b32 q, %8, %8;\n\t"
+                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %7, p;\n\t"
+                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %4, %7, q;\n\t"
+                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %5, %6, %7, q;\n\t"
+                      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+                      "}" ::"r"(d_tmem),
+                      "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(idesc), "r"(acc), "r"(ebar)
+                      : "memory");
+                } else {
+                  asm volatile(
+                      "{\n\t"
+                      ".reg .pred p, q;\n\t"
+                      "setp.ne.b32 p, %8, 0;\n\t"
+                      "setp.eq.b32 q, %8, %8;\n\t"
+                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %7, p;\n\t"
+                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %4, %7, q;\n\t"
+                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %5, %6, %7, q;\n\t"
+                      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%9], %10;\n\t"
+                      "}" ::"r"(d_tmem),
+                      "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(idesc), "r"(acc), "r"(ebar), "h"(kMask)
+                      : "memory");
+                }
+              } else {  // diagnostic: fewer products
+                umma_bf16(d_tmem, a0, b0, idesc, acc);
+                if (dbg_products >= 2) umma_bf16(d_tmem, a1, b1, idesc, 1u);
+                if constexpr (CS == 1) umma_commit(ebar);
+                else umma_commit_mc(ebar, kMask);
+              }
+              acc = 1;
+              if (ktr) trace[kbase + 2] = clock64();
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
           }
           umma_commit(bar(BAR_DFULL + db));  // accumulator complete -> epilogue
@@ -296,28 +364,28 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
     const int row = (warp & 3) * 32 + lane;     // TMEM lane == ray within the tile
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
     uint32_t gp = 0;
+    auto encode_tile = [&](long long ray_) {
+      float enc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) enc[i] = 0.0f;
+      if (ray_ < n_rays) encode_ray(cfg, rays + ray_ * cfg.c_in, enc, 1);
+#pragma unroll
+      for (int kg = 0; kg < 4; ++kg) {
+        uint4 hi, lo;
+        split8(enc + kg * 8, hi, lo);
+        *reinterpret_cast<uint4*>(smem + OFF_A_HI + a_slot(row, kg)) = hi;
+        *reinterpret_cast<uint4*>(smem + OFF_A_LO + a_slot(row, kg)) = lo;
+      }
+      fence_async_smem();
+      mbar_arrive(bar(BAR_AREADY + 0));
+    };
+    const int last_hidden = cfg.mlp_layers - 2;
     for (long long iter = 0; iter < n_iters; ++iter) {
       const long long tile = (iter * n_clusters + cluster_id) * CS + crank;  // may be >= n_tiles: fully masked
       const long long ray = tile * BM + row;
       // ---- encode (RayParam + WindowedPE), split, write chunk 0 (group 0 only) ----
-      if (grp == 0) {
-        float enc[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) enc[i] = 0.0f;
-        if (ray < n_rays) encode_ray(cfg, rays + ray * cfg.c_in, enc, 1);
-#pragma unroll
-        for (int kg = 0; kg < 4; ++kg) {
-          uint4 hi, lo;
-          split8(enc + kg * 8, hi, lo);
-          *reinterpret_cast<uint4*>(smem + OFF_A_HI + a_slot(row, kg)) = hi;
-          *reinterpret_cast<uint4*>(smem + OFF_A_LO + a_slot(row, kg)) = lo;
-        }
-        fence_async_smem();
-        mbar_arrive(bar(BAR_AREADY + 0));
-      }
-      float* out_row = heads + ray * (long long)cfg.mlp_out;
-      const bool row_ok = ray < n_rays;
-      const bool vec_ok = (cfg.mlp_out & 3) == 0;
+      // The first tile is encoded here; every later tile was already encoded during the previous tile's last layer.
+      if (grp == 0 && iter == 0) encode_tile(ray);
       for (int p = 0; p < n_passes; ++p, ++gp) {
         const TcPass& P = pk.passes[p];
         const uint32_t db = gp & 1, use = gp >> 1;
@@ -326,68 +394,80 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
         tc_fence_after();
         const uint32_t t_addr = tmem_base + lane_base + db * 256;
         const float* bias = s_bias + P.bias_off;
-        const int nchunks = P.is_final ? (P.n + 31) / 32 : 8;
-        // this group's last chunk; a group with no chunk in this pass releases the accumulator right away
-        const int last_j = (grp < nchunks) ? ((nchunks - 1 - grp) / EPI_GROUPS) * EPI_GROUPS + grp : -1;
-        if (last_j < 0) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
-        for (int j = grp; j < nchunks; j += EPI_GROUPS) {
-          uint32_t v[32];
-          tmem_ld32(t_addr + j * 32, v);
-          if (j == last_j) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
-          // bias of these 32 columns (shared-memory broadcast, 16-byte loads), folded into v
-          {
-            const float4* b4 = reinterpret_cast<const float4*>(bias + j * 32);
+        if (!P.is_final) {
+          // Hidden layer: the groups sweep the eight 32-column chunks together, each taking 32/EPI_GROUPS columns of every
+          // chunk, so chunk j of the next A operand is complete (a_ready[1+j]) after 1/8 of the epilogue and the next
+          // layer's MMAs trail the epilogue chunk by chunk.
+          constexpr int CW = 32 / EPI_GROUPS;  // columns per group per chunk (16)
+          for (int j = 0; j < 8; ++j) {
+            uint32_t v[16];
+            tmem_ld16(t_addr + j * 32 + grp * CW, v);
+            if (j == 7) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+            const float4* b4 = reinterpret_cast<const float4*>(bias + j * 32 + grp * CW);
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              const float4 b = b4[i4];
-              v[i4 * 4 + 0] = __float_as_uint(__uint_as_float(v[i4 * 4 + 0]) + b.x);
-              v[i4 * 4 + 1] = __float_as_uint(__uint_as_float(v[i4 * 4 + 1]) + b.y);
-              v[i4 * 4 + 2] = __float_as_uint(__uint_as_float(v[i4 * 4 + 2]) + b.z);
-              v[i4 * 4 + 3] = __float_as_uint(__uint_as_float(v[i4 * 4 + 3]) + b.w);
-            }
-          }
-          if (!P.is_final) {
-#pragma unroll
-            for (int kg = 0; kg < 4; ++kg) {
+            for (int kg = 0; kg < CW / 8; ++kg) {
+              const float4 ba = b4[kg * 2], bb = b4[kg * 2 + 1];
+              const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
               float x[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float t = __uint_as_float(v[kg * 8 + i]);
+                const float t = __uint_as_float(v[kg * 8 + i]) + bv[i];
                 x[i] = fmaxf(t, t * cfg.leaky_slope);  // LeakyReLU, slope in (0,1)
               }
               uint4 hi, lo;
               split8(x, hi, lo);
-              const uint32_t off = (1 + j) * CHUNK_BYTES + a_slot(row, kg);
+              const uint32_t off = (1 + j) * CHUNK_BYTES + a_slot(row, grp * (CW / 8) + kg);
               *reinterpret_cast<uint4*>(smem + OFF_A_HI + off) = hi;
               *reinterpret_cast<uint4*>(smem + OFF_A_LO + off) = lo;
             }
             fence_async_smem();
             mbar_arrive(bar(BAR_AREADY + 1 + j));
             if (tid == 0 && j == 0) TR(iter, p, 5);
-            if (lane == 0 && (warp & 3) == 0 && j == 7) TR(iter, p, 6);
-          } else {
-            // last layer: this thread owns 32 consecutive channel-major columns of its ray = one 128-byte line
-            const int c0 = P.out_col0 + j * 32;
-            const int nvalid = min(min(32, P.n - j * 32), cfg.mlp_out - c0);
-            if (row_ok && nvalid > 0) {
-              if (vec_ok) {
+            if (tid == 0 && j == 7) TR(iter, p, 6);
+          }
+          // Chunk 0 (the encoded input) is read by the first and the skip layer only; once the last hidden layer's
+          // accumulator is complete both have retired, so the next tile's rays are encoded now, under the last layer's
+          // MMAs, instead of after its epilogue.
+          if (P.layer == last_hidden && grp == 0 && iter + 1 < n_iters) {
+            const long long ntile = ((iter + 1) * n_clusters + cluster_id) * CS + crank;
+            encode_tile(ntile * BM + row);
+          }
+        } else {
+          // Last layer: 8-column slices are transposed through a 1 KB per-warp staging area so that every global store
+          // instruction writes four 32-byte row segments (whole sectors).
+          float* stg = reinterpret_cast<float*>(smem + OFF_STG) + warp * 256;
+          const int nslice = (P.n + 7) / 8;
+          const int last_h = (grp < nslice) ? ((nslice - 1 - grp) / EPI_GROUPS) * EPI_GROUPS + grp : -1;
+          if (last_h < 0) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+          const int sub = lane >> 3, cidx = lane & 7;  // store mapping: 4 rows x 8 columns per instruction
+          const long long row0 = tile * BM + (warp & 3) * 32;
+          for (int h = grp; h < nslice; h += EPI_GROUPS) {
+            uint32_t v[8];
+            tmem_ld8(t_addr + h * 8, v);
+            if (h == last_h) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+            const float4* b4 = reinterpret_cast<const float4*>(bias + h * 8);
+            const float4 ba = b4[0], bb = b4[1];
+            // row `lane` holds its 8 values at stg[lane*8 + (i ^ (lane>>2 & 7))]: conflict-free for both phases
+            const int sw = (lane >> 2) & 7;
+            stg[lane * 8 + (0 ^ sw)] = __uint_as_float(v[0]) + ba.x;
+            stg[lane * 8 + (1 ^ sw)] = __uint_as_float(v[1]) + ba.y;
+            stg[lane * 8 + (2 ^ sw)] = __uint_as_float(v[2]) + ba.z;
+            stg[lane * 8 + (3 ^ sw)] = __uint_as_float(v[3]) + ba.w;
+            stg[lane * 8 + (4 ^ sw)] = __uint_as_float(v[4]) + bb.x;
+            stg[lane * 8 + (5 ^ sw)] = __uint_as_float(v[5]) + bb.y;
+            stg[lane * 8 + (6 ^ sw)] = __uint_as_float(v[6]) + bb.z;
+            stg[lane * 8 + (7 ^ sw)] = __uint_as_float(v[7]) + bb.w;
+            __syncwarp();
+            const int col = P.out_col0 + h * 8 + cidx;
+            const bool col_ok = (h * 8 + cidx < P.n) && (col < cfg.mlp_out);
+            float* dst = heads + (row0 + sub) * (long long)cfg.mlp_out + col;
 #pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                  if (i4 * 4 < nvalid) {
-                    float4 o;
-                    o.x = __uint_as_float(v[i4 * 4 + 0]);
-                    o.y = __uint_as_float(v[i4 * 4 + 1]);
-                    o.z = __uint_as_float(v[i4 * 4 + 2]);
-                    o.w = __uint_as_float(v[i4 * 4 + 3]);
-                    *reinterpret_cast<float4*>(out_row + c0 + i4 * 4) = o;
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < nvalid) out_row[c0 + i] = __uint_as_float(v[i]);
-              }
+            for (int rr = 0; rr < 32; rr += 4) {
+              const int r = rr + sub;
+              const float o = stg[r * 8 + (cidx ^ ((r >> 2) & 7))];
+              if (col_ok && row0 + r < n_rays) dst[(long long)rr * cfg.mlp_out] = o;
             }
+            __syncwarp();
           }
         }
       }
@@ -520,8 +600,8 @@ static cudaError_t launch_mlp_tc_cs(const hr_config& cfg, const MlpTcPack& pk, c
   unsigned long long* trace = nullptr;
   const bool want_trace = getenv("HR_TC_TRACE") != nullptr;
   if (want_trace) {
-    cudaMalloc((void**)&trace, 16 * 8 * sizeof(unsigned long long));
-    cudaMemset(trace, 0, 16 * 8 * sizeof(unsigned long long));
+    cudaMalloc((void**)&trace, 256 * sizeof(unsigned long long));
+    cudaMemset(trace, 0, 256 * sizeof(unsigned long long));
   }
   long long tiles = (n + tc::BM - 1) / tc::BM;
   long long want = (tiles + CS - 1) / CS * CS;
@@ -544,7 +624,7 @@ static cudaError_t launch_mlp_tc_cs(const hr_config& cfg, const MlpTcPack& pk, c
   lc.numAttrs = 1;
   cudaError_t le = cudaLaunchKernelEx(&lc, mlp_tc_kernel<CS>, cfg, pk, rays, heads, n, dbg_products, dbg_load_lo, trace);
   if (want_trace) {
-    unsigned long long h[16 * 8];
+    unsigned long long h[256];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(trace);
@@ -553,6 +633,15 @@ static cudaError_t launch_mlp_tc_cs(const hr_config& cfg, const MlpTcPack& pk, c
     for (int p = 0; p < pk.n_passes; ++p) {
       fprintf(stderr, "[tc-trace] %2d:", p);
       for (int e = 0; e < 7; ++e) fprintf(stderr, " %8lld", h[p * 8 + e] ? (long long)(h[p * 8 + e] - t0) : -1LL);
+      fprintf(stderr, "\n");
+    }
+    for (int blk = 0; blk < 2; ++blk) {
+      fprintf(stderr, "[tc-trace] k-steps of pass %d: (before_wait_full, wait_cost, issue_cost) rel. to first\n[tc-trace]  ", blk ? 6 : 2);
+      unsigned long long b0 = h[128 + blk * 64];
+      for (int k = 0; k < 16; ++k) {
+        const unsigned long long* e = h + 128 + blk * 64 + k * 4;
+        fprintf(stderr, "(%lld,%lld,%lld) ", (long long)(e[0] - b0), (long long)(e[1] - e[0]), (long long)(e[2] - e[1]));
+      }
       fprintf(stderr, "\n");
     }
   }
@@ -564,7 +653,7 @@ cudaError_t launch_mlp_tc(const hr_config& cfg, const MlpTcPack& pk, const float
   // diagnostic knobs (profiling only; defaults = the product path)
   static const int dbg_products = getenv("HR_TC_PRODUCTS") ? atoi(getenv("HR_TC_PRODUCTS")) : 3;
   static const int dbg_load_lo = getenv("HR_TC_LOAD_LO") ? atoi(getenv("HR_TC_LOAD_LO")) : 1;
-  static const int cluster = getenv("HR_TC_CLUSTER") ? atoi(getenv("HR_TC_CLUSTER")) : 2;
+  static const int cluster = getenv("HR_TC_CLUSTER") ? atoi(getenv("HR_TC_CLUSTER")) : 1;
   if (cluster == 4) return launch_mlp_tc_cs<4>(cfg, pk, rays, heads, n, num_sms, stream, dbg_products, dbg_load_lo);
   if (cluster == 2) return launch_mlp_tc_cs<2>(cfg, pk, rays, heads, n, num_sms, stream, dbg_products, dbg_load_lo);
   return launch_mlp_tc_cs<1>(cfg, pk, rays, heads, n, num_sms, stream, dbg_products, dbg_load_lo);
