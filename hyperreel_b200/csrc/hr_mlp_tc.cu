@@ -223,6 +223,10 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
   if constexpr (CS > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can target them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // Let the dependent (render) grid start launching now: its CTAs run their prologue and park in griddepcontrol.wait
+  // until this grid has completed and flushed, so their launch latency is hidden behind this kernel.
+  if (dbg_products & 0x100) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  dbg_products &= 0xff;
 
   const long long n_tiles = (n_rays + BM - 1) / BM;
   const int n_passes = pk.n_passes;
@@ -608,8 +612,14 @@ static cudaError_t launch_mlp_tc_cs(const hr_config& cfg, const MlpTcPack& pk, c
   long long cap = (long long)(num_sms / CS) * CS;
   int grid = (int)(want < cap ? want : cap);
   if (grid < CS) grid = CS;
-  cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
+  static bool attr_set[64] = {false};  // per template instance and device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3((unsigned)grid);
   lc.blockDim = dim3(tc::NTHREADS);
@@ -653,10 +663,12 @@ cudaError_t launch_mlp_tc(const hr_config& cfg, const MlpTcPack& pk, const float
   // diagnostic knobs (profiling only; defaults = the product path)
   static const int dbg_products = getenv("HR_TC_PRODUCTS") ? atoi(getenv("HR_TC_PRODUCTS")) : 3;
   static const int dbg_load_lo = getenv("HR_TC_LOAD_LO") ? atoi(getenv("HR_TC_LOAD_LO")) : 1;
+  static const int pdl_early = getenv("HR_PDL_EARLY") ? atoi(getenv("HR_PDL_EARLY")) : 0;  // measured: parked dependents slow this kernel
+  const int prod_flags = dbg_products | (pdl_early ? 0x100 : 0);
   static const int cluster = getenv("HR_TC_CLUSTER") ? atoi(getenv("HR_TC_CLUSTER")) : 1;
-  if (cluster == 4) return launch_mlp_tc_cs<4>(cfg, pk, rays, heads, n, num_sms, stream, dbg_products, dbg_load_lo);
-  if (cluster == 2) return launch_mlp_tc_cs<2>(cfg, pk, rays, heads, n, num_sms, stream, dbg_products, dbg_load_lo);
-  return launch_mlp_tc_cs<1>(cfg, pk, rays, heads, n, num_sms, stream, dbg_products, dbg_load_lo);
+  if (cluster == 4) return launch_mlp_tc_cs<4>(cfg, pk, rays, heads, n, num_sms, stream, prod_flags, dbg_load_lo);
+  if (cluster == 2) return launch_mlp_tc_cs<2>(cfg, pk, rays, heads, n, num_sms, stream, prod_flags, dbg_load_lo);
+  return launch_mlp_tc_cs<1>(cfg, pk, rays, heads, n, num_sms, stream, prod_flags, dbg_load_lo);
 }
 
 }  // namespace hr

@@ -11,6 +11,8 @@
 //     LDG.128 (reference: F.grid_sample calls in nlf/nets/tensorf_dynamic.py:287-371 and
 //     nlf/nets/tensorf_no_sample.py:47-126).
 // Nothing per-sample ever goes to HBM: rays (4*c_in B) + sample-net heads in, rgb (12 B) out.
+#include <cstdlib>
+
 #include "hr_common.cuh"
 
 namespace hr {
@@ -222,6 +224,10 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
 #pragma unroll
     for (int i = 0; i < NT; ++i) G[i] = s_basis[qc * NT + fcol[i]];
   }
+
+  // Programmatic dependent launch: everything above overlaps the tail of the sample-net kernel; its heads become
+  // visible here.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const float inv_x = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[3], cfg.aabb[0]));  // invaabbSize (tensorf_base.py:292)
   const float inv_y = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[4], cfg.aabb[1]));
@@ -614,15 +620,22 @@ static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const Ren
   long long ctas_needed = (n + kWarpsPerCta - 1) / kWarpsPerCta;
   long long grid = ctas_needed < (long long)num_sms * kMinCtasPerSm * 2 ? ctas_needed : (long long)num_sms * kMinCtasPerSm * 2;
   if (grid < 1) grid = 1;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(kWarpsPerCta * 32);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // may start while the sample-net kernel drains
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  static const int use_pdl = getenv("HR_PDL") ? atoi(getenv("HR_PDL")) : 0;  // measured: no gain on B200 (profiles/r1_notes.md)
+  lc.numAttrs = use_pdl ? 1 : 0;
   if (so) {
-    render_kernel<SPL, DYN, C0, C1, C2, SHADE, true><<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(
-        cfg, dv, tabs, rays, heads, rgb, n, *so);
-  } else {
-    StageOut none{nullptr, nullptr, nullptr, nullptr};
-    render_kernel<SPL, DYN, C0, C1, C2, SHADE, false><<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(
-        cfg, dv, tabs, rays, heads, rgb, n, none);
+    return cudaLaunchKernelEx(&lc, render_kernel<SPL, DYN, C0, C1, C2, SHADE, true>, cfg, dv, tabs, rays, heads, rgb, n, *so);
   }
-  return cudaGetLastError();
+  StageOut none{nullptr, nullptr, nullptr, nullptr};
+  return cudaLaunchKernelEx(&lc, render_kernel<SPL, DYN, C0, C1, C2, SHADE, false>, cfg, dv, tabs, rays, heads, rgb, n, none);
 }
 
 template <int SPL, bool DYN, int C0, int C1, int C2>
