@@ -17,6 +17,7 @@
 //   warp 17    MMA issuer: one lane issues tcgen05.mma / tcgen05.commit, trailing the epilogue chunk by chunk
 //              (a_ready barriers per 32-column chunk), with two 256-column TMEM accumulators ping-ponged
 //              across layers so layer l+1's MMAs overlap layer l's epilogue.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 
 #include <cstdio>
@@ -31,7 +32,7 @@ namespace hr {
 namespace tc {
 
 constexpr int BM = 128;            // rays per tile (UMMA M)
-constexpr int NSTAGE = 4;          // weight ring depth
+constexpr int NSTAGE = 3;          // weight ring depth (weights were never late with 4; 3 frees 16 KB for staging)
 constexpr int STAGE_BYTES = 16384; // one k-step image: N<=256 rows x 16 k x (hi+lo) bf16
 constexpr int CHUNK_BYTES = 8192;  // one A chunk: 128 rows x 32 k bf16
 constexpr int NCHUNK = 9;          // chunk 0 = encoded input (32, zero padded), chunks 1..8 = hidden 256
@@ -46,8 +47,8 @@ constexpr int OFF_A_LO = OFF_A_HI + NCHUNK * CHUNK_BYTES;   // 73728
 constexpr int OFF_B = OFF_A_LO + NCHUNK * CHUNK_BYTES;      // 147456
 constexpr int OFF_BIAS = OFF_B + NSTAGE * STAGE_BYTES;      // 212992
 constexpr int OFF_BAR = OFF_BIAS + BIAS_FLOATS * 4;         // 223232
-constexpr int OFF_STG = OFF_BAR + 256;                      // 223488: last-layer transpose staging, 1 KB per epilogue warp
-constexpr int SMEM_BYTES = OFF_STG + EPI_WARPS * 1024;      // 231680 (of 232448 available)
+constexpr int OFF_STG = OFF_BAR + 256;                      // last-layer transpose staging, 2 KB per epilogue warp
+constexpr int SMEM_BYTES = OFF_STG + EPI_WARPS * 2048;      // 223488 (of 232448 available)
 
 // barrier slots (8 bytes each) inside OFF_BAR
 constexpr int BAR_FULL = 0;                 // [NSTAGE]
@@ -195,7 +196,8 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
 template <int CS>
 __global__ void __launch_bounds__(tc::NTHREADS, 1)
 mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ MlpTcPack pk, const float* __restrict__ rays,
-              float* __restrict__ heads, long long n_rays, int dbg_products, int dbg_load_lo, unsigned long long* trace) {
+              float* __restrict__ heads, long long n_rays, int dbg_products, int dbg_load_lo, unsigned long long* trace,
+              const __grid_constant__ CUtensorMap heads_map, int use_tma_store) {
   using namespace tc;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -437,41 +439,78 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
             encode_tile(ntile * BM + row);
           }
         } else {
-          // Last layer: 8-column slices are transposed through a 1 KB per-warp staging area so that every global store
-          // instruction writes four 32-byte row segments (whole sectors).
-          float* stg = reinterpret_cast<float*>(smem + OFF_STG) + warp * 256;
-          const int nslice = (P.n + 7) / 8;
+          // Last layer: 16-column slices are transposed through a 2 KB per-warp staging area so that every global store
+          // instruction writes two 64-byte row segments.
+          float* stg = reinterpret_cast<float*>(smem + OFF_STG) + warp * 512;
+          const int nslice = (P.n + 15) / 16;
           const int last_h = (grp < nslice) ? ((nslice - 1 - grp) / EPI_GROUPS) * EPI_GROUPS + grp : -1;
           if (last_h < 0) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
-          const int sub = lane >> 3, cidx = lane & 7;  // store mapping: 4 rows x 8 columns per instruction
+          const int half = lane >> 4, cidx = lane & 15;  // store mapping: 2 rows x 16 columns per instruction
           const long long row0 = tile * BM + (warp & 3) * 32;
-          for (int h = grp; h < nslice; h += EPI_GROUPS) {
-            uint32_t v[8];
-            tmem_ld8(t_addr + h * 8, v);
-            if (h == last_h) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
-            const float4* b4 = reinterpret_cast<const float4*>(bias + h * 8);
-            const float4 ba = b4[0], bb = b4[1];
-            // row `lane` holds its 8 values at stg[lane*8 + (i ^ (lane>>2 & 7))]: conflict-free for both phases
-            const int sw = (lane >> 2) & 7;
-            stg[lane * 8 + (0 ^ sw)] = __uint_as_float(v[0]) + ba.x;
-            stg[lane * 8 + (1 ^ sw)] = __uint_as_float(v[1]) + ba.y;
-            stg[lane * 8 + (2 ^ sw)] = __uint_as_float(v[2]) + ba.z;
-            stg[lane * 8 + (3 ^ sw)] = __uint_as_float(v[3]) + ba.w;
-            stg[lane * 8 + (4 ^ sw)] = __uint_as_float(v[4]) + bb.x;
-            stg[lane * 8 + (5 ^ sw)] = __uint_as_float(v[5]) + bb.y;
-            stg[lane * 8 + (6 ^ sw)] = __uint_as_float(v[6]) + bb.z;
-            stg[lane * 8 + (7 ^ sw)] = __uint_as_float(v[7]) + bb.w;
-            __syncwarp();
-            const int col = P.out_col0 + h * 8 + cidx;
-            const bool col_ok = (h * 8 + cidx < P.n) && (col < cfg.mlp_out);
-            float* dst = heads + (row0 + sub) * (long long)cfg.mlp_out + col;
+          if (use_tma_store) {
+            // TMEM -> registers -> 32 x 16 box in shared memory (row = lane, 64-byte rows) -> one TMA tensor store per box;
+            // rows past n_rays / columns past mlp_out are clipped by the tensor map.
+            const uint32_t stg_s = sbase + OFF_STG + warp * 2048;
+            for (int h = grp; h < nslice; h += EPI_GROUPS) {
+              uint32_t v[16];
+              tmem_ld16(t_addr + h * 16, v);
+              if (h == last_h) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+              const float4* b4 = reinterpret_cast<const float4*>(bias + h * 16);
+              // the previous box of this warp must have been read out of the staging buffer
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
 #pragma unroll
-            for (int rr = 0; rr < 32; rr += 4) {
-              const int r = rr + sub;
-              const float o = stg[r * 8 + (cidx ^ ((r >> 2) & 7))];
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 b = b4[i4];
+                float4 o;
+                o.x = __uint_as_float(v[i4 * 4 + 0]) + b.x;
+                o.y = __uint_as_float(v[i4 * 4 + 1]) + b.y;
+                o.z = __uint_as_float(v[i4 * 4 + 2]) + b.z;
+                o.w = __uint_as_float(v[i4 * 4 + 3]) + b.w;
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_s + lane * 64 + i4 * 16), "f"(o.x), "f"(o.y),
+                             "f"(o.z), "f"(o.w)
+                             : "memory");
+              }
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                const int x = P.out_col0 + h * 16;
+                const int y = (int)(tile * BM + (warp & 3) * 32);
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                 reinterpret_cast<uint64_t>(&heads_map)),
+                             "r"(x), "r"(y), "r"(stg_s)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
+          } else {
+          for (int h = grp; h < nslice; h += EPI_GROUPS) {
+            uint32_t v[16];
+            tmem_ld16(t_addr + h * 16, v);
+            if (h == last_h) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+            const float4* b4 = reinterpret_cast<const float4*>(bias + h * 16);
+            // row `lane` keeps element i at stg[lane*16 + (i ^ ((lane>>1)&15))]: conflict-free for both phases
+            const int sw = (lane >> 1) & 15;
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 b = b4[i4];
+              stg[lane * 16 + ((i4 * 4 + 0) ^ sw)] = __uint_as_float(v[i4 * 4 + 0]) + b.x;
+              stg[lane * 16 + ((i4 * 4 + 1) ^ sw)] = __uint_as_float(v[i4 * 4 + 1]) + b.y;
+              stg[lane * 16 + ((i4 * 4 + 2) ^ sw)] = __uint_as_float(v[i4 * 4 + 2]) + b.z;
+              stg[lane * 16 + ((i4 * 4 + 3) ^ sw)] = __uint_as_float(v[i4 * 4 + 3]) + b.w;
+            }
+            __syncwarp();
+            const int col = P.out_col0 + h * 16 + cidx;
+            const bool col_ok = (h * 16 + cidx < P.n) && (col < cfg.mlp_out);
+            float* dst = heads + (row0 + half) * (long long)cfg.mlp_out + col;
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 2) {
+              const int r = rr + half;
+              const float o = stg[r * 16 + (cidx ^ ((r >> 1) & 15))];
               if (col_ok && row0 + r < n_rays) dst[(long long)rr * cfg.mlp_out] = o;
             }
             __syncwarp();
+          }
           }
         }
       }
@@ -479,6 +518,7 @@ mlp_tc_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Mlp
   }
 
   // ---- teardown ----
+  if (warp < EPI_WARPS && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // TMA stores landed
   tc_fence_before();
   __syncthreads();
   if constexpr (CS > 1) cluster_sync_all();  // no CTA leaves while a peer can still signal its barriers
@@ -632,7 +672,35 @@ static cudaError_t launch_mlp_tc_cs(const hr_config& cfg, const MlpTcPack& pk, c
   at[0].val.clusterDim.z = 1;
   lc.attrs = at;
   lc.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&lc, mlp_tc_kernel<CS>, cfg, pk, rays, heads, n, dbg_products, dbg_load_lo, trace);
+  // tensor map of the heads scratch [n rays][mlp_out] fp32 for the last layer's TMA stores (box 16 cols x 32 rows)
+  CUtensorMap hmap;
+  memset(&hmap, 0, sizeof(hmap));
+  int use_tma = 0;
+  static const int want_tma = getenv("HR_TC_TMA_STORE") ? atoi(getenv("HR_TC_TMA_STORE")) : 1;
+  if (want_tma && (cfg.mlp_out % 4) == 0 && ((uintptr_t)heads % 16) == 0) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+          qres == cudaDriverEntryPointSuccess)
+        encode = (EncodeFn)fn;
+    }
+    if (encode) {
+      cuuint64_t gdim[2] = {(cuuint64_t)cfg.mlp_out, (cuuint64_t)n};
+      cuuint64_t gstride[1] = {(cuuint64_t)cfg.mlp_out * sizeof(float)};
+      cuuint32_t box[2] = {16, 32};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = encode(&hmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)heads, gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      use_tma = (r == CUDA_SUCCESS) ? 1 : 0;
+    }
+  }
+  cudaError_t le = cudaLaunchKernelEx(&lc, mlp_tc_kernel<CS>, cfg, pk, rays, heads, n, dbg_products, dbg_load_lo, trace, hmap, use_tma);
   if (want_trace) {
     unsigned long long h[256];
     cudaStreamSynchronize(stream);
