@@ -18,7 +18,8 @@
 namespace hr {
 cudaError_t launch_render(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
                           const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
-                          cudaStream_t stream);
+                          cudaStream_t stream, unsigned char* rgb8);
+cudaError_t launch_generate_rays(const hr_camera& cam, int c_in, long long first, long long n, float* out, cudaStream_t st);
 }  // namespace hr
 
 static thread_local std::string g_err;
@@ -386,11 +387,11 @@ int64_t hr_workspace_bytes(const hr_handle* h, int64_t n_rays) {
 }
 
 static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, float* mlp_out, const hr::StageOut* so,
-                       void* workspace, int64_t ws_bytes, cudaStream_t st) {
+                       void* workspace, int64_t ws_bytes, cudaStream_t st, unsigned char* rgb8 = nullptr) {
   if (!h) return fail("hr_render: null handle");
   if (!h->uploaded) return fail("hr_render: parameters not uploaded (call hr_upload)");
   if (n == 0) return 0;
-  if (!rays || !rgb || !workspace) return fail("hr_render: null buffer");
+  if (!rays || (!rgb && !rgb8) || !workspace) return fail("hr_render: null buffer");
   if (ws_bytes < hr_workspace_bytes(h, n)) return fail("hr_render: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)hr_workspace_bytes(h, n));
   if (((uintptr_t)workspace & 15) != 0) return fail("hr_render: workspace must be 16-byte aligned");
   float* heads = (float*)workspace;
@@ -410,7 +411,7 @@ static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, f
   }
   if (e != cudaSuccess) return fail("sample-net launch failed: %s", cudaGetErrorString(e));
   if (timing) { CK(cudaEventRecord(em.b, st)); CK(cudaEventRecord(er.a, st)); }
-  e = hr::launch_render(c, h->dv, h->tabs, rays, heads, rgb, n, so, h->num_sms, st);
+  e = hr::launch_render(c, h->dv, h->tabs, rays, heads, rgb, n, so, h->num_sms, st, rgb8);
   if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
   if (timing) {
     CK(cudaEventRecord(er.b, st));
@@ -440,6 +441,65 @@ int hr_render_stages(hr_handle* h, const float* rays, int64_t n_rays, float* rgb
   return render_impl(h, rays, n_rays, rgb, mlp_out, &so, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int hr_render_to8b(hr_handle* h, const float* rays, int64_t n_rays, uint8_t* rgb8, void* workspace, int64_t workspace_bytes,
+                   void* stream) {
+  if (h) CK(cudaSetDevice(h->device));
+  if (!rgb8) return fail("hr_render_to8b: null output");
+  return render_impl(h, rays, n_rays, nullptr, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream, rgb8);
+}
+
+int hr_generate_rays(const hr_camera* cam, int32_t c_in, int64_t first_pixel, int64_t n_pixels, float* rays_out, void* stream) {
+  if (!cam || !rays_out) return fail("hr_generate_rays: null argument");
+  if (c_in != 6 && c_in != 8) return fail("hr_generate_rays: c_in must be 6 or 8");
+  if (cam->width < 1 || cam->height < 1) return fail("hr_generate_rays: bad image size");
+  if (first_pixel < 0 || n_pixels < 0 || first_pixel + n_pixels > (int64_t)cam->width * cam->height)
+    return fail("hr_generate_rays: pixel range outside the image");
+  cudaError_t e = hr::launch_generate_rays(*cam, c_in, first_pixel, n_pixels, rays_out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail("hr_generate_rays: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int hr_render_frame_to8b_host(hr_handle* h, const hr_camera* cam, uint8_t* rgb8_host, int64_t chunk) {
+  if (!h || !cam || !rgb8_host) return fail("hr_render_frame_to8b_host: null argument");
+  if (!h->uploaded) return fail("hr_render_frame_to8b_host: parameters not uploaded");
+  CK(cudaSetDevice(h->device));
+  const hr_config& c = h->cfg;
+  const int64_t n_rays = (int64_t)cam->width * cam->height;
+  if (chunk <= 0) chunk = 262144;
+  if (chunk > n_rays) chunk = n_rays;
+  HostPipe& P = h->pipe;
+  // device scratch per slot: rays, 8-bit tile (stored in the rgb slot), workspace
+  if (P.chunk < chunk) {
+    for (int i = 0; i < 3; ++i) {
+      if (P.d_rays[i]) cudaFree(P.d_rays[i]);
+      if (P.d_rgb[i]) cudaFree(P.d_rgb[i]);
+      if (P.d_ws[i]) cudaFree(P.d_ws[i]);
+      P.d_rays[i] = P.d_rgb[i] = nullptr; P.d_ws[i] = nullptr;
+      if (!P.streams[i]) CK(cudaStreamCreateWithFlags(&P.streams[i], cudaStreamNonBlocking));
+    }
+    P.ws_bytes = hr_workspace_bytes(h, chunk);
+    for (int i = 0; i < 3; ++i) {
+      CK(cudaMalloc((void**)&P.d_rays[i], (size_t)chunk * 8 * sizeof(float)));
+      CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)chunk * 3 * sizeof(float)));
+      CK(cudaMalloc(&P.d_ws[i], (size_t)P.ws_bytes));
+    }
+    P.chunk = chunk;
+  }
+  int slot = 0;
+  for (int64_t off = 0; off < n_rays; off += chunk, slot = (slot + 1) % 3) {
+    const int64_t m = (n_rays - off < chunk) ? (n_rays - off) : chunk;
+    cudaStream_t st = P.streams[slot];
+    cudaError_t e = hr::launch_generate_rays(*cam, c.c_in, off, m, P.d_rays[slot], st);
+    if (e != cudaSuccess) return fail("ray generation failed: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    int rc = render_impl(h, P.d_rays[slot], m, nullptr, nullptr, nullptr, P.d_ws[slot], P.ws_bytes, st, (unsigned char*)P.d_rgb[slot]);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(rgb8_host + off * 3, P.d_rgb[slot], (size_t)m * 3, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < 3; ++i) CK(cudaStreamSynchronize(P.streams[i]));
+  return 0;
+}
+
 int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* rgb_host, int64_t chunk) {
   if (!h) return fail("hr_render_host: null handle");
   if (!h->uploaded) return fail("hr_render_host: parameters not uploaded");
@@ -460,7 +520,7 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
     }
     P.ws_bytes = hr_workspace_bytes(h, chunk);
     for (int i = 0; i < 3; ++i) {
-      CK(cudaMalloc((void**)&P.d_rays[i], (size_t)chunk * c.c_in * sizeof(float)));
+      CK(cudaMalloc((void**)&P.d_rays[i], (size_t)chunk * 8 * sizeof(float)));
       CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)chunk * 3 * sizeof(float)));
       CK(cudaMalloc(&P.d_ws[i], (size_t)P.ws_bytes));
     }

@@ -186,7 +186,8 @@ template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool STAGES>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (C1 + C2 == 0) ? 3 : 2)
 render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Derived dv,
               const __grid_constant__ RenderTabs tabs, const float* __restrict__ rays,
-              const float* __restrict__ heads, float* __restrict__ rgb_out, long long n_rays, StageOut so) {
+              const float* __restrict__ heads, float* __restrict__ rgb_out, long long n_rays, StageOut so,
+              unsigned char* __restrict__ rgb8_out) {
   constexpr int NT = C0 + C1 + C2;
   constexpr int ROWS = (SHADE == HR_SHADE_SH) ? 9 : 1;
   constexpr int ROUNDS = 4 * SPL;
@@ -605,7 +606,12 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       float v = accq + ((lane == 0) ? accB[0] : ((lane == 1) ? accB[1] : accB[2]));
       if (cfg.white_bg && !cfg.black_bg) v = v + (1.0f - accw);
       if (cfg.clamp_output) v = fminf(fmaxf(v, 0.0f), 1.0f);
-      rgb_out[ray * 3 + lane] = v;
+      if (rgb8_out != nullptr) {
+        // to8b (utils/__init__.py:47): (255 * clip(x, 0, 1)).astype(uint8) -- truncation
+        rgb8_out[ray * 3 + lane] = (unsigned char)(int)__fmul_rn(255.0f, fminf(fmaxf(v, 0.0f), 1.0f));
+      } else {
+        rgb_out[ray * 3 + lane] = v;
+      }
     }
   }
 }
@@ -613,7 +619,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
 template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE>
 static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
                               const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, unsigned char* rgb8) {
   constexpr int ROWS = (SHADE == HR_SHADE_SH) ? 9 : 1;
   constexpr int NT = C0 + C1 + C2;
   size_t smem = 3 * (size_t)ROWS * NT * sizeof(float);
@@ -632,46 +638,46 @@ static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const Ren
   static const int use_pdl = getenv("HR_PDL") ? atoi(getenv("HR_PDL")) : 0;  // measured: no gain on B200 (profiles/r1_notes.md)
   lc.numAttrs = use_pdl ? 1 : 0;
   if (so) {
-    return cudaLaunchKernelEx(&lc, render_kernel<SPL, DYN, C0, C1, C2, SHADE, true>, cfg, dv, tabs, rays, heads, rgb, n, *so);
+    return cudaLaunchKernelEx(&lc, render_kernel<SPL, DYN, C0, C1, C2, SHADE, true>, cfg, dv, tabs, rays, heads, rgb, n, *so, rgb8);
   }
   StageOut none{nullptr, nullptr, nullptr, nullptr};
-  return cudaLaunchKernelEx(&lc, render_kernel<SPL, DYN, C0, C1, C2, SHADE, false>, cfg, dv, tabs, rays, heads, rgb, n, none);
+  return cudaLaunchKernelEx(&lc, render_kernel<SPL, DYN, C0, C1, C2, SHADE, false>, cfg, dv, tabs, rays, heads, rgb, n, none, rgb8);
 }
 
 template <int SPL, bool DYN, int C0, int C1, int C2>
 static cudaError_t launch_shade(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
                                 const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, unsigned char* rgb8) {
   if (cfg.shading == HR_SHADE_SH)
-    return launch_one<SPL, DYN, C0, C1, C2, HR_SHADE_SH>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream);
-  return launch_one<SPL, DYN, C0, C1, C2, HR_SHADE_RGB>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream);
+    return launch_one<SPL, DYN, C0, C1, C2, HR_SHADE_SH>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
+  return launch_one<SPL, DYN, C0, C1, C2, HR_SHADE_RGB>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
 }
 
 template <int SPL, bool DYN>
 static cudaError_t launch_comps(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
                                 const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, unsigned char* rgb8) {
   const int c0 = cfg.n_sigma[0], c1 = cfg.n_sigma[1], c2 = cfg.n_sigma[2];
   if (c0 == 8 && c1 == 0 && c2 == 0)
-    return launch_shade<SPL, DYN, 8, 0, 0>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream);
+    return launch_shade<SPL, DYN, 8, 0, 0>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
   if (c0 == 8 && c1 == 4 && c2 == 4)
-    return launch_shade<SPL, DYN, 8, 4, 4>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream);
+    return launch_shade<SPL, DYN, 8, 4, 4>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
   if (c0 == 8 && c1 == 8 && c2 == 8)
-    return launch_shade<SPL, DYN, 8, 8, 8>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream);
+    return launch_shade<SPL, DYN, 8, 8, 8>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
   return cudaErrorInvalidValue;
 }
 
 // Entry used by hr_api.cu.  Returns cudaErrorInvalidValue for an unsupported component layout.
 cudaError_t launch_render(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
                           const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, unsigned char* rgb8) {
   const bool two = cfg.n_samples > 32;
   if (cfg.dynamic) {
-    return two ? launch_comps<2, true>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream)
-               : launch_comps<1, true>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream);
+    return two ? launch_comps<2, true>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8)
+               : launch_comps<1, true>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
   }
-  return two ? launch_comps<2, false>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream)
-             : launch_comps<1, false>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream);
+  return two ? launch_comps<2, false>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8)
+             : launch_comps<1, false>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
 }
 
 }  // namespace hr

@@ -147,6 +147,38 @@ class LightfieldModel(nn.Module):
         L.check(self._lib.hr_render_host(self._handle, rays_host.data_ptr(), n, rgb_host.data_ptr(), chunk))
         return rgb_host
 
+    def render_to8b(self, rays: torch.Tensor) -> torch.Tensor:
+        """rays [N,C] on the device -> uint8 rgb [N,3] on the device: the composite with ``to8b``
+        (utils/__init__.py:47) fused into the render kernel's epilogue (hr_render_to8b)."""
+        if self.training:
+            raise RuntimeError("hyperreel_b200.LightfieldModel implements the eval()/render path only; call .eval()")
+        rays = self._check_rays(rays)
+        n = rays.shape[0]
+        out = torch.empty((n, 3), device=rays.device, dtype=torch.uint8)
+        if n == 0:
+            return out
+        self._ensure_uploaded(rays.device)
+        ws = self._workspace(n, rays.device)
+        stream = torch.cuda.current_stream(rays.device).cuda_stream
+        L.check(self._lib.hr_render_to8b(self._handle, rays.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        return out
+
+    def render_frame_to8b(self, camera, out_host: Optional[torch.Tensor] = None, chunk: int = 0) -> torch.Tensor:
+        """One whole frame: rays generated on the device from ``camera`` (hyperreel_b200.camera.Camera), rendered,
+        packed to 8 bit and copied into a pinned host image [H, W, 3] uint8 (hr_render_frame_to8b_host) -- one iteration of
+        the reference's validation_video / viewer loop without the per-frame 32 B/ray upload."""
+        if self.training:
+            raise RuntimeError("hyperreel_b200.LightfieldModel implements the eval()/render path only; call .eval()")
+        H, W = int(camera.height), int(camera.width)
+        if out_host is None:
+            out_host = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True)
+        if out_host.is_cuda or out_host.dtype != torch.uint8 or out_host.numel() != H * W * 3 or not out_host.is_contiguous():
+            raise ValueError("out_host must be a contiguous uint8 host tensor of H*W*3 elements")
+        self._ensure_uploaded(torch.device("cuda", self._device_index if self._device_index is not None else torch.cuda.current_device()))
+        cam = camera.to_c()
+        L.check(self._lib.hr_render_frame_to8b_host(self._handle, C.byref(cam), out_host.data_ptr(), chunk))
+        return out_host
+
     def timing(self, enable: bool = True):
         L.check(self._lib.hr_timing_enable(self._handle, int(enable)))
         L.check(self._lib.hr_timing_reset(self._handle))

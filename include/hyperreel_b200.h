@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HR_ABI_VERSION 3
+#define HR_ABI_VERSION 4
 
 #define HR_MAX_GROUPS 4   /* ray-parameterisation groups feeding the sample net (ray.py:235-263) */
 #define HR_MAX_LAYERS 10  /* Linear layers of the sample net (mlp.py:127-154) */
@@ -192,6 +192,39 @@ int hr_render_stages(hr_handle* h, const float* rays, int64_t n_rays, float* rgb
  * `chunk` rays (0 = default), overlaps H2D / kernels / D2H on internal streams and returns when the
  * rgb is on the host. */
 int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* rgb_host, int64_t chunk);
+
+/* ---- the step before the path: camera -> rays on the device ----
+ * Replaces: get_coords_from_camera / get_coords (datasets/base.py:485-518, datasets/technicolor.py:360-396), i.e.
+ * get_ray_directions_K + get_rays (+ get_ndc_rays_fx_fy) of utils/ray_utils.py:98-164, executed on the CPU by the
+ * reference and uploaded with .cuda() per frame (nlf/__init__.py:828-834).  Pixel p = y*width + x, row-major like
+ * kornia.create_meshgrid(H, W, normalized_coordinates=False). */
+typedef struct hr_camera {
+  float c2w[12];            /* camera-to-world, row-major 3x4 (pose[:3,:4])                         */
+  float fx, fy, cx, cy;     /* K[0,0], K[1,1], K[0,2], K[1,2]                                       */
+  int32_t width, height;    /* W, H                                                                 */
+  int32_t centered_pixels;  /* +0.5 pixel offset (ray_utils.py:103-104)                             */
+  int32_t flipped;          /* sign of the y direction (ray_utils.py:108)                           */
+  int32_t normalize;        /* get_rays(normalize=True) (ray_utils.py:127-128)                      */
+  int32_t use_ndc;          /* get_ndc_rays_fx_fy (ray_utils.py:137-164) with H, W, fx, fy of this camera */
+  float ndc_near;           /* dataset.near                                                         */
+  float cam_idx, time;      /* channels 6 and 7 when c_in == 8 (technicolor.py:389-393)             */
+} hr_camera;
+
+/* rays_out [n_pixels, c_in] fp32 device, for pixels first_pixel .. first_pixel + n_pixels - 1; c_in is 6 or 8. */
+int hr_generate_rays(const hr_camera* cam, int32_t c_in, int64_t first_pixel, int64_t n_pixels, float* rays_out,
+                     void* stream);
+
+/* ---- the step after the path: 8-bit packing ----
+ * Replaces: to8b(x) = (255 * clip(x, 0, 1)).astype(uint8) (utils/__init__.py:47) applied to the rendered frame before
+ * it is written or displayed (nlf/__init__.py:857-891, utils/gui_utils.py:174-186).  Same as hr_render, but the fused
+ * kernel's epilogue stores rgb8 [n,3] uint8 (3 B/ray instead of 12 B/ray leave the GPU). */
+int hr_render_to8b(hr_handle* h, const float* rays, int64_t n_rays, uint8_t* rgb8, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
+/* Whole frame on HOST output: rays generated on the device from `cam`, rendered, packed to 8 bit, copied into the
+ * (pinned) host buffer rgb8_host [width*height, 3]; synchronous.  Replaces one iteration of validation_video /
+ * NeRFGUI.test_step (nlf/__init__.py:828-891, utils/gui_utils.py:139-212). */
+int hr_render_frame_to8b_host(hr_handle* h, const hr_camera* cam, uint8_t* rgb8_host, int64_t chunk);
 
 /* Number of kernels hr_render launched since creation (bench.py's gpu_launches). */
 int64_t hr_launch_count(const hr_handle* h);

@@ -106,7 +106,15 @@ def install():
         return m
 
     if "kornia" not in sys.modules:
-        stub("kornia", create_meshgrid=None)
+        def create_meshgrid(height, width, normalized_coordinates=True, device="cpu", dtype=torch.float32):
+            # functional stand-in for kornia.utils.create_meshgrid (pixel-coordinate form only): [1, H, W, 2] = (x, y)
+            assert not normalized_coordinates
+            xs = torch.linspace(0, width - 1, width, dtype=dtype)
+            ys = torch.linspace(0, height - 1, height, dtype=dtype)
+            gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+            return torch.stack([gx, gy], -1)[None]
+
+        stub("kornia", create_meshgrid=create_meshgrid)
     if "plyfile" not in sys.modules:
         stub("plyfile", PlyData=None, PlyElement=None)
     if "skimage" not in sys.modules:

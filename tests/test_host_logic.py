@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_c_abi_library_loads_and_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "hyperreel_b200.h")).read()
-    declared = set(re.findall(r"\b(hr_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(hr_[a-z0-9_]+)\s*\(", header))
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
     lib = L.load_library()
     for name in declared:
@@ -41,6 +41,26 @@ def test_ctypes_struct_matches_header_field_order():
             if n:
                 fields.append(n)
     assert fields == [f[0] for f in L.hr_config._fields_]
+
+
+def test_camera_struct_matches_header_field_order():
+    header = open(os.path.join(ROOT, "include", "hyperreel_b200.h")).read()
+    body = header[header.index("typedef struct hr_camera {"):header.index("} hr_camera;")]
+    fields = []
+    for line in body.splitlines()[1:]:
+        line = line.split("/*")[0].strip()
+        if not line:
+            continue
+        decl = line.rstrip(";")
+        for n in decl.split(None, 1)[1].split(","):
+            n = re.sub(r"\[.*\]", "", n).strip()
+            if n:
+                fields.append(n)
+    assert fields == [f[0] for f in L.hr_camera._fields_]
+    cam = hb.Camera(pose=[[1, 0, 0, 0.5], [0, 1, 0, -1], [0, 0, 1, 2]], K=[[100, 0, 32], [0, 90, 24], [0, 0, 1]], width=64,
+                    height=48, time=0.5, cam_idx=2, use_ndc=True, ndc_near=0.7).to_c()
+    assert (cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height) == (100.0, 90.0, 32.0, 24.0, 64, 48)
+    assert list(cam.c2w)[3::4] == [0.5, -1.0, 2.0] and cam.use_ndc == 1 and abs(cam.ndc_near - 0.7) < 1e-7
 
 
 def test_create_without_gpu_fails_loudly():
