@@ -287,7 +287,9 @@ int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
     h->simt.Np[l] = Np;
   }
   if (!rc && c.mlp_mode == HR_MLP_BF16X3_TC) {
-    rc = hr::pack_mlp_tc(h, p, w_dev, b_dev, st);
+    // HR_TC_V=1 keeps the first tensor-core layout (hr_mlp_tc.cu) selectable for A/B measurements
+    static const int tc_version = getenv("HR_TC_V") ? atoi(getenv("HR_TC_V")) : 2;
+    rc = (tc_version == 1) ? hr::pack_mlp_tc(h, p, w_dev, b_dev, st) : hr::pack_mlp_tc2(h, p, w_dev, b_dev, st);
     if (!rc) h->tc_ready = true;
   }
 
@@ -405,7 +407,8 @@ static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, f
   cudaError_t e;
   if (c.mlp_mode == HR_MLP_BF16X3_TC) {
     if (!h->tc_ready) return fail("hr_render: tensor-core pack missing");
-    e = hr::launch_mlp_tc(c, h->tc, rays, heads, n, h->num_sms, st);
+    e = (h->tc.version == 2) ? hr::launch_mlp_tc2(c, h->tc, rays, heads, n, h->num_sms, st)
+                             : hr::launch_mlp_tc(c, h->tc, rays, heads, n, h->num_sms, st);
   } else {
     e = hr::launch_mlp_simt(c, h->simt, rays, heads, n, h->num_sms, st);
   }

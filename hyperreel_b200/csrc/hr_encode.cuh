@@ -4,10 +4,13 @@
 
 namespace hr {
 
-// RayPredictionEmbedding input encoding for one ray (nlf/embedding/ray.py:320-326).
-// Writes cfg.mlp_in values with stride `stride` starting at dst.
-__device__ __forceinline__ void encode_ray(const hr_config& cfg, const float* __restrict__ ray, float* dst, int stride) {
-  int k = 0;
+// RayPredictionEmbedding input encoding for one ray (nlf/embedding/ray.py:320-326), feature by feature:
+// emit(k, value) is called for the features of every work item (identity block or one frequency band) whose running
+// index is congruent to `part` modulo `nparts`, so several threads can share one ray.  k < cfg.mlp_in.
+template <class Emit>
+__device__ __forceinline__ void encode_ray_features(const hr_config& cfg, const float* __restrict__ ray, int part, int nparts,
+                                                    Emit&& emit) {
+  int k = 0, item = 0;
   for (int g = 0; g < cfg.n_groups; ++g) {
     const hr_encode_group& G = cfg.groups[g];
     float v[8];
@@ -45,16 +48,31 @@ __device__ __forceinline__ void encode_ray(const hr_config& cfg, const float* __
       for (int i = 0; i < dims; ++i) v[i] = r[i];
     }
     // WindowedPE with all windows open (pe.py:210-221): [x | sin(f1 x) | cos(f1 x) | sin(f2 x) | ...]
-    if (!G.exclude_identity)
-      for (int i = 0; i < dims; ++i) dst[(k++) * stride] = v[i];
+    if (!G.exclude_identity) {
+      if ((item++ % nparts) == part)
+        for (int i = 0; i < dims; ++i) emit(k + i, v[i]);
+      k += dims;
+    }
     float freq = 1.0f;
     for (int f = 0; f < G.n_freqs; ++f) {
       freq = __fmul_rn(freq, G.freq_mult);  // freq_multiplier ** (f+1), exact for 2.0
-      float bf = __fmul_rn(G.base_mult, freq);
-      for (int i = 0; i < dims; ++i) dst[(k++) * stride] = sinf(__fmul_rn(bf, v[i]));
-      for (int i = 0; i < dims; ++i) dst[(k++) * stride] = cosf(__fmul_rn(bf, v[i]));
+      if ((item++ % nparts) == part) {
+        const float bf = __fmul_rn(G.base_mult, freq);
+        for (int i = 0; i < dims; ++i) {
+          float sv, cv;
+          sincosf(__fmul_rn(bf, v[i]), &sv, &cv);
+          emit(k + i, sv);
+          emit(k + dims + i, cv);
+        }
+      }
+      k += 2 * dims;
     }
   }
+}
+
+// Writes cfg.mlp_in values with stride `stride` starting at dst.
+__device__ __forceinline__ void encode_ray(const hr_config& cfg, const float* __restrict__ ray, float* dst, int stride) {
+  encode_ray_features(cfg, ray, 0, 1, [&](int k, float val) { dst[k * stride] = val; });
 }
 
 

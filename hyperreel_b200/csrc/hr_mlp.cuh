@@ -22,7 +22,7 @@ struct MlpSimtPack {
 
 // tcgen05 path (HR_MLP_BF16X3_TC): see hr_mlp_tc.cu.  A "pass" is one accumulator's worth of output columns
 // (a hidden layer, or <=256 columns of the last layer); its weights are stored as n_chunks*2 k-step images.
-#define HR_TC_MAX_PASSES 16
+#define HR_TC_MAX_PASSES 24
 struct TcPass {
   int layer;        // Linear layer index
   int n;            // output columns of this pass (multiple of 16, <= 256)
@@ -39,6 +39,7 @@ struct MlpTcPack {
   long long wpack_bytes;
   int n_passes;
   int bias_count;
+  int version;         // 1 = hr_mlp_tc.cu (full-width passes, A in shared memory), 2 = hr_mlp_tc2.cu (half passes, A_hi in TMEM)
   TcPass passes[HR_TC_MAX_PASSES];
 };
 
@@ -48,10 +49,13 @@ cudaError_t launch_mlp_simt(const hr_config& cfg, const MlpSimtPack& pk, const f
 
 cudaError_t launch_mlp_tc(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
                           int num_sms, cudaStream_t stream);
+cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
+                           int num_sms, cudaStream_t stream);
 }  // namespace hr
 
 struct hr_handle;
 struct hr_params;
 namespace hr {
 int pack_mlp_tc(hr_handle* h, const hr_params* p, const float* const* w_dev, const float* const* b_dev, cudaStream_t st);
+int pack_mlp_tc2(hr_handle* h, const hr_params* p, const float* const* w_dev, const float* const* b_dev, cudaStream_t st);
 }

@@ -26,12 +26,12 @@
 
 #include "hr_encode.cuh"
 #include "hr_handle.h"
+#include "hr_tc_prims.cuh"
 
 namespace hr {
 
 namespace tc {
 
-constexpr int BM = 128;            // rays per tile (UMMA M)
 constexpr int NSTAGE = 3;          // weight ring depth (weights were never late with 4; 3 frees 16 KB for staging)
 constexpr int STAGE_BYTES = 16384; // one k-step image: N<=256 rows x 16 k x (hi+lo) bf16
 constexpr int CHUNK_BYTES = 8192;  // one A chunk: 128 rows x 32 k bf16
@@ -57,137 +57,6 @@ constexpr int BAR_AREADY = BAR_EMPTY + NSTAGE; // [NCHUNK]
 constexpr int BAR_DFULL = BAR_AREADY + NCHUNK; // [2]
 constexpr int BAR_DEMPTY = BAR_DFULL + 2;      // [2]
 constexpr int BAR_TMEMPTR = BAR_DEMPTY + 2;    // 4-byte TMEM base address lives in this slot
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, no-swizzle UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-//   [0,14) start>>4 | [16,30) leading (K-direction core-matrix) byte offset>>4 | [32,46) stride (M/N-direction) byte
-//   offset>>4 | [46,48) version = 1 | [61,64) layout type = 0 (SWIZZLE_NONE)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-// Instruction descriptor (InstrDescriptor): c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B,
-// n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
-__device__ __forceinline__ uint32_t umma_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Offset (bytes) of the 16-byte row slot holding k-group kg of row `row` inside a 128-row x 32-k chunk.
-__device__ __forceinline__ uint32_t a_slot(int row, int kg) { return (uint32_t)((kg * 16 + (row >> 3)) * 128 + (row & 7) * 16); }
-
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
-    float r0 = x[2 * i] - __low2float(hh);
-    float r1 = x[2 * i + 1] - __high2float(hh);
-    __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
-    h[i] = *reinterpret_cast<uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<uint32_t*>(&ll);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
 
 }  // namespace tc
 
@@ -576,10 +445,49 @@ __global__ void pack_tc_pass(const float* __restrict__ W, const float* __restric
   }
 }
 
+
+// Tensor map of the heads scratch [n rays][mlp_out] fp32, box = 16 columns x 32 rows (one epilogue warp's slice).
+// The encoder comes from the driver through the runtime (no link-time libcuda dependency).  False = not available.
+bool make_heads_map(CUtensorMap* hmap, const float* heads, int mlp_out, long long n) {
+  memset(hmap, 0, sizeof(*hmap));
+  if ((mlp_out % 4) != 0 || ((uintptr_t)heads % 16) != 0) return false;
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = (EncodeFn)fn;
+  }
+  if (!encode) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)mlp_out, (cuuint64_t)n};
+  cuuint64_t gstride[1] = {(cuuint64_t)mlp_out * sizeof(float)};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(hmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)heads, gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+void launch_pack_tc_pass(const float* W, const float* b, uint8_t* dst, float* bias_dst, int n, int first_chunk, int n_chunks,
+                         int in_src, int mlp_in, int is_skip, int out_rows, int perm_S, int perm_stride, int out_col0,
+                         cudaStream_t st) {
+  long long total = (long long)n_chunks * 2 * n * 16 + n;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  pack_tc_pass<<<grid, 256, 0, st>>>(W, b, dst, bias_dst, n, first_chunk, n_chunks, in_src, mlp_in, is_skip, 0, out_rows, perm_S,
+                                     perm_stride, out_col0);
+}
+
 int pack_mlp_tc(hr_handle* h, const hr_params*, const float* const* w_dev, const float* const* b_dev, cudaStream_t st) {
   const hr_config& c = h->cfg;
   MlpTcPack& pk = h->tc;
   memset(&pk, 0, sizeof(pk));
+  pk.version = 1;
   if (c.mlp_width != 256) return hr_fail("tensor-core sample net: width must be 256");
   if (c.mlp_in > 32) return hr_fail("tensor-core sample net: encoded input wider than 32");
   const int L = c.mlp_layers;
@@ -622,12 +530,9 @@ int pack_mlp_tc(hr_handle* h, const hr_params*, const float* const* w_dev, const
     const bool last = (l == L - 1), skip = (l == c.mlp_skip), first = (l == 0);
     const int in_src = first ? c.mlp_in : (skip ? c.mlp_in + 256 : 256);
     const int out_rows = last ? c.mlp_out : 256;
-    long long total = (long long)P.n_chunks * 2 * P.n * 16 + P.n;
-    int grid = (int)((total + 255) / 256);
-    if (grid > 148 * 16) grid = 148 * 16;
-    pack_tc_pass<<<grid, 256, 0, st>>>(w_dev[l], b_dev[l], wp + off, bp + P.bias_off, P.n, P.first_chunk, P.n_chunks, in_src,
-                                       c.mlp_in, skip ? 1 : 0, first ? 1 : 0, out_rows, last ? c.n_samples : 0,
-                                       c.head_stride, P.out_col0);
+    launch_pack_tc_pass(w_dev[l], b_dev[l], wp + off, bp + P.bias_off, P.n, P.first_chunk, P.n_chunks, in_src, c.mlp_in,
+                        skip ? 1 : 0, out_rows, last ? c.n_samples : 0, c.head_stride, P.out_col0, st);
+    (void)first;
     off += (size_t)P.n_chunks * 2 * P.n * 64;
   }
   e = cudaGetLastError();
@@ -674,32 +579,8 @@ static cudaError_t launch_mlp_tc_cs(const hr_config& cfg, const MlpTcPack& pk, c
   lc.numAttrs = 1;
   // tensor map of the heads scratch [n rays][mlp_out] fp32 for the last layer's TMA stores (box 16 cols x 32 rows)
   CUtensorMap hmap;
-  memset(&hmap, 0, sizeof(hmap));
-  int use_tma = 0;
   static const int want_tma = getenv("HR_TC_TMA_STORE") ? atoi(getenv("HR_TC_TMA_STORE")) : 1;
-  if (want_tma && (cfg.mlp_out % 4) == 0 && ((uintptr_t)heads % 16) == 0) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
-          qres == cudaDriverEntryPointSuccess)
-        encode = (EncodeFn)fn;
-    }
-    if (encode) {
-      cuuint64_t gdim[2] = {(cuuint64_t)cfg.mlp_out, (cuuint64_t)n};
-      cuuint64_t gstride[1] = {(cuuint64_t)cfg.mlp_out * sizeof(float)};
-      cuuint32_t box[2] = {16, 32};
-      cuuint32_t estr[2] = {1, 1};
-      CUresult r = encode(&hmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)heads, gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      use_tma = (r == CUDA_SUCCESS) ? 1 : 0;
-    }
-  }
+  const int use_tma = (want_tma && make_heads_map(&hmap, heads, cfg.mlp_out, n)) ? 1 : 0;
   cudaError_t le = cudaLaunchKernelEx(&lc, mlp_tc_kernel<CS>, cfg, pk, rays, heads, n, dbg_products, dbg_load_lo, trace, hmap, use_tma);
   if (want_trace) {
     unsigned long long h[256];

@@ -35,11 +35,15 @@ def main():
     ap.add_argument("--rays", default="65536,262144,1048576,4194304")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--mlp", default="bf16x3")
+    ap.add_argument("--only", default="", help="comma-separated workload names (default: all)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     flush = torch.empty((512 << 20) // 4, dtype=torch.float32, device=dev)
     rows = []
+    only = [w for w in args.only.split(",") if w]
     for wname, (builtin, over, note) in WORKLOADS.items():
+        if only and wname not in only:
+            continue
         cfg, ds = hb.configs.get(builtin, **over)
         sig = hb.lower(cfg, ds)
         sd = seeded_state_dict(sig, seed=11, density_gain=30.0)
