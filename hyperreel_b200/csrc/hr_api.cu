@@ -243,9 +243,12 @@ int hr_create(const hr_config* cfg, int device, hr_handle** out) {
   return 0;
 }
 
+static void drop_host_graph(hr_handle* h);
+
 int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
   if (!h || !p) return fail("hr_upload: null argument");
   CK(cudaSetDevice(h->device));
+  drop_host_graph(h);
   cudaStream_t st = (cudaStream_t)stream;
   const hr_config& c = h->cfg;
   // release any previous pack
@@ -388,6 +391,13 @@ int64_t hr_workspace_bytes(const hr_handle* h, int64_t n_rays) {
   return (b + 255) / 256 * 256 + 256;
 }
 
+// The cached hr_render_host graph holds kernel parameters by value: drop it whenever they may have changed.
+static void drop_host_graph(hr_handle* h) {
+  if (h->pipe.graph) cudaGraphExecDestroy(h->pipe.graph);
+  h->pipe.graph = nullptr;
+  h->pipe.g_rays = nullptr; h->pipe.g_rgb = nullptr; h->pipe.g_n = 0; h->pipe.g_chunk = 0;
+}
+
 static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, float* mlp_out, const hr::StageOut* so,
                        void* workspace, int64_t ws_bytes, cudaStream_t st, unsigned char* rgb8 = nullptr) {
   if (!h) return fail("hr_render: null handle");
@@ -468,11 +478,12 @@ int hr_render_frame_to8b_host(hr_handle* h, const hr_camera* cam, uint8_t* rgb8_
   CK(cudaSetDevice(h->device));
   const hr_config& c = h->cfg;
   const int64_t n_rays = (int64_t)cam->width * cam->height;
-  if (chunk <= 0) chunk = 262144;
+  if (chunk <= 0) chunk = (h->cfg.mlp_mode == HR_MLP_BF16X3_TC) ? (int64_t)h->num_sms * 128 * 14 : 262144;  // whole tile waves
   if (chunk > n_rays) chunk = n_rays;
   HostPipe& P = h->pipe;
   // device scratch per slot: rays, 8-bit tile (stored in the rgb slot), workspace
   if (P.chunk < chunk) {
+    drop_host_graph(h);
     for (int i = 0; i < 3; ++i) {
       if (P.d_rays[i]) cudaFree(P.d_rays[i]);
       if (P.d_rgb[i]) cudaFree(P.d_rgb[i]);
@@ -509,11 +520,14 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
   if (n_rays == 0) return 0;
   if (!rays_host || !rgb_host) return fail("hr_render_host: null buffer");
   CK(cudaSetDevice(h->device));
-  if (chunk <= 0) chunk = 32768;
+  const hr_config& c = h->cfg;
+  // default chunk: one full wave of 128-ray tiles of the tensor-core sample net (148 x 128 = 18 944 rays on B200), so
+  // splitting a batch for copy/compute overlap adds no partially filled wave; 32 768 for the CUDA-core net
+  if (chunk <= 0) chunk = (c.mlp_mode == HR_MLP_BF16X3_TC) ? (int64_t)h->num_sms * 128 : 32768;
   if (chunk > n_rays) chunk = n_rays;
   HostPipe& P = h->pipe;
-  const hr_config& c = h->cfg;
   if (P.chunk < chunk) {
+    drop_host_graph(h);
     for (int i = 0; i < 3; ++i) {
       if (P.d_rays[i]) cudaFree(P.d_rays[i]);
       if (P.d_rgb[i]) cudaFree(P.d_rgb[i]);
@@ -529,15 +543,56 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
     }
     P.chunk = chunk;
   }
-  int slot = 0;
-  for (int64_t off = 0; off < n_rays; off += chunk, slot = (slot + 1) % 3) {
-    int64_t m = (n_rays - off < chunk) ? (n_rays - off) : chunk;
-    cudaStream_t st = P.streams[slot];
-    CK(cudaMemcpyAsync(P.d_rays[slot], rays_host + off * c.c_in, (size_t)m * c.c_in * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = render_impl(h, P.d_rays[slot], m, P.d_rgb[slot], nullptr, nullptr, P.d_ws[slot], P.ws_bytes, st);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(rgb_host + off * 3, P.d_rgb[slot], (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  // The pipeline of one call: chunk i runs H2D -> sample net -> render -> D2H on stream i % 3.
+  auto enqueue = [&]() -> int {
+    int slot = 0;
+    for (int64_t off = 0; off < n_rays; off += chunk, slot = (slot + 1) % 3) {
+      int64_t m = (n_rays - off < chunk) ? (n_rays - off) : chunk;
+      cudaStream_t st = P.streams[slot];
+      CK(cudaMemcpyAsync(P.d_rays[slot], rays_host + off * c.c_in, (size_t)m * c.c_in * sizeof(float), cudaMemcpyHostToDevice, st));
+      int rc = render_impl(h, P.d_rays[slot], m, P.d_rgb[slot], nullptr, nullptr, P.d_ws[slot], P.ws_bytes, st);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(rgb_host + off * 3, P.d_rgb[slot], (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+  };
+  static const int use_graph = getenv("HR_HOST_GRAPH") ? atoi(getenv("HR_HOST_GRAPH")) : 1;
+  const int64_t n_chunks = (n_rays + chunk - 1) / chunk;
+  if (use_graph && !h->timing && n_chunks > 1) {
+    // Launch-bound when issued call by call (5 driver calls per chunk against ~75 us of GPU work per chunk): capture the
+    // whole multi-stream pipeline once per (buffers, size) signature and replay it with a single graph launch.
+    if (!(P.graph && P.g_rays == rays_host && P.g_rgb == rgb_host && P.g_n == n_rays && P.g_chunk == chunk)) {
+      drop_host_graph(h);
+      if (!P.fork_ev) {
+        CK(cudaEventCreateWithFlags(&P.fork_ev, cudaEventDisableTiming));
+        for (int i = 0; i < 3; ++i) CK(cudaEventCreateWithFlags(&P.join_ev[i], cudaEventDisableTiming));
+      }
+      const int64_t launches_before = h->launches;
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(P.streams[0], cudaStreamCaptureModeRelaxed));
+      CK(cudaEventRecord(P.fork_ev, P.streams[0]));
+      for (int i = 1; i < 3; ++i) CK(cudaStreamWaitEvent(P.streams[i], P.fork_ev, 0));
+      int rc = enqueue();
+      for (int i = 1; i < 3; ++i) {
+        cudaEventRecord(P.join_ev[i], P.streams[i]);
+        cudaStreamWaitEvent(P.streams[0], P.join_ev[i], 0);
+      }
+      cudaError_t ce = cudaStreamEndCapture(P.streams[0], &g);
+      h->launches = launches_before;  // capture enqueued nothing; the replay below is what runs
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (ce != cudaSuccess) return fail("hr_render_host: graph capture failed: %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&P.graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) { P.graph = nullptr; return fail("hr_render_host: graph instantiate failed: %s", cudaGetErrorString(ce)); }
+      P.g_rays = rays_host; P.g_rgb = rgb_host; P.g_n = n_rays; P.g_chunk = chunk;
+    }
+    CK(cudaGraphLaunch(P.graph, P.streams[0]));
+    h->launches += 2 * n_chunks;
+    CK(cudaStreamSynchronize(P.streams[0]));
+    return 0;
   }
+  int rc = enqueue();
+  if (rc) return rc;
   for (int i = 0; i < 3; ++i) CK(cudaStreamSynchronize(P.streams[i]));
   return 0;
 }
@@ -587,6 +642,11 @@ int hr_destroy(hr_handle* h) {
   drop_events(h->ev_render);
   drop_events(h->ev_mlp);
   for (int i = 0; i < 3; ++i) {
+    if (i == 0) {
+      drop_host_graph(h);
+      if (h->pipe.fork_ev) cudaEventDestroy(h->pipe.fork_ev);
+    }
+    if (h->pipe.join_ev[i]) cudaEventDestroy(h->pipe.join_ev[i]);
     if (h->pipe.d_rays[i]) cudaFree(h->pipe.d_rays[i]);
     if (h->pipe.d_rgb[i]) cudaFree(h->pipe.d_rgb[i]);
     if (h->pipe.d_ws[i]) cudaFree(h->pipe.d_ws[i]);

@@ -19,6 +19,12 @@ struct HostPipe {
   float* d_rgb[3] = {nullptr, nullptr, nullptr};
   void* d_ws[3] = {nullptr, nullptr, nullptr};
   int64_t ws_bytes = 0;
+  // hr_render_host replays its whole copy/kernel pipeline as one CUDA graph while the call signature repeats
+  cudaGraphExec_t graph = nullptr;
+  const void* g_rays = nullptr;
+  void* g_rgb = nullptr;
+  int64_t g_n = 0, g_chunk = 0;
+  cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
 };
 
 struct hr_handle {

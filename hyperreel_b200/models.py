@@ -212,10 +212,16 @@ class LightfieldModel(nn.Module):
         return self._ws
 
     def _param_version(self):
-        return tuple((p._version, p.data_ptr()) for p in self.parameters()) + tuple(self.color_model.net.gridSize.tolist())
+        # version counters + storage addresses only: no device synchronisation on the per-call path
+        net = self.color_model.net
+        return tuple((p._version, p.data_ptr()) for p in self.parameters()) + tuple(
+            (b._version, b.data_ptr()) for b in (net.aabb, net.gridSize))
 
     def _ensure_uploaded(self, dev: torch.device):
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        ver = self._param_version()
+        if self._handle and self._device_index == idx and self._uploaded_version == ver:
+            return
         # aabb is checkpoint state (it changes when the reference shrinks the grid, tensorf_base.py:1190-1232)
         aabb = [float(v) for v in self.color_model.net.aabb.detach().cpu().reshape(-1).tolist()]
         if aabb != [float(self.sig.cfg.aabb[i]) for i in range(6)]:
@@ -231,9 +237,6 @@ class LightfieldModel(nn.Module):
             L.check(self._lib.hr_create(C.byref(self.sig.cfg), idx, C.byref(self._handle)))
             self._device_index = idx
             self._uploaded_version = None
-        ver = self._param_version()
-        if self._uploaded_version == ver:
-            return
         P = L.hr_params()
         keep = []  # keep tensors alive until the upload has been enqueued and synchronised
 

@@ -108,6 +108,32 @@ def test_host_buffer_entry_point_matches_device_path():
     assert torch.equal(host, dev)
 
 
+def test_host_entry_point_graph_replay_tracks_buffers_and_reupload():
+    """hr_render_host replays a captured CUDA graph while (buffers, size, chunk) repeat: new ray values in the same
+    pinned buffer and re-uploaded parameters must both show up in the replayed result."""
+    case = build_case("technicolor_trained", n=6000)
+    for mode in ("fp32", "bf16x3"):
+        render = make_render(case, mlp_mode=mode)
+        rays_a = case.rays.clone()
+        rays_b = case.rays.flip(0).contiguous()
+        pinned = rays_a.clone().pin_memory()
+        out = torch.empty((rays_a.shape[0], 3), dtype=torch.float32).pin_memory()
+        render.model.render_host(pinned, out, chunk=1500)
+        assert torch.equal(out, render(rays_a.cuda())["rgb"].cpu())
+        pinned.copy_(rays_b)
+        render.model.render_host(pinned, out, chunk=1500)  # same signature: graph replay
+        assert torch.equal(out, render(rays_b.cuda())["rgb"].cpu())
+        with torch.no_grad():
+            for prm in render.parameters():
+                if prm.dim() == 2 and prm.shape[0] == 256:  # hidden Linear weights
+                    prm.mul_(0.5)
+        render.model.mark_dirty()
+        render.model.render_host(pinned, out, chunk=1500)  # re-upload drops the graph
+        assert torch.equal(out, render(rays_b.cuda())["rgb"].cpu())
+        out2 = render.model.render_host(pinned, chunk=6000)  # single chunk: plain path
+        assert torch.equal(out2, out)
+
+
 def test_empty_batch_and_errors():
     case = build_case("shiny_tiny", n=8)
     render = make_render(case)
