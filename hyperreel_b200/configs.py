@@ -12,6 +12,8 @@ depth_range: tensorf_dynamic.py:49-50, contract.py:121-125, primitive.py:371-373
 """
 from __future__ import annotations
 
+import copy
+
 from typing import Dict, Tuple
 
 from .config import Cfg, to_cfg
@@ -201,4 +203,59 @@ def get(name: str, **overrides) -> Tuple[Cfg, dict]:
     for k in ("num_keyframes", "num_frames"):
         if k in overrides:
             ds[k] = int(overrides[k])
+    for v in _as_list(overrides.get("variant")):
+        _apply_variant(cfg, v)
     return cfg, ds
+
+
+def _as_list(v):
+    return [] if v is None else ([v] if isinstance(v, str) else list(v))
+
+
+def _apply_variant(cfg: Cfg, variant: str) -> None:
+    """Schema-level edits that turn a built-in into the other shipped pipeline families: the result is
+    still a valid reference config (the parity tests build the unmodified reference from it)."""
+    emb = cfg.embedding.embeddings
+    pred, it = emb.ray_prediction_0, emb.ray_intersect_0.intersect
+    if variant == "basic_pe":  # technicolor_z_plane_{small,tiny,large}.yaml: `pe: {type: basic}`
+        for g in pred.params.values():
+            if "pe" in g and g.pe is not None:
+                g.pe = to_cfg({"type": "basic", "n_freqs": int(g.pe.n_freqs), "freq_multiplier": 2.0})
+    elif variant == "bbox":  # technicolor_z_plane_world.yaml:143-147
+        it.contract = to_cfg({"type": "bbox", "contract_samples": True, "bbox_min": [-2.0, -2.0, 0.5],
+                              "bbox_max": [2.0, 2.0, -2.5]})
+    elif variant == "z_depth":
+        it.contract = to_cfg({"type": "z_depth", "contract_samples": True, "contract_end_radius": 3.0})
+    elif variant == "cylinder":  # donerf_cylinder.yaml / immersive_cylinder.yaml: `type: cylinder`
+        if it.type != "sphere":
+            raise ValueError("the cylinder variant starts from a sphere pipeline")
+        it.type = "cylinder"
+    elif variant == "sphere":  # immersive_sphere.yaml: a dynamic (keyframe) pipeline behind sphere primitives
+        if it.type != "z_plane":
+            raise ValueError("the sphere variant starts from a z_plane pipeline")
+        it.type = "sphere"
+        it.origin_scale_factor = 0.0
+        pred.outputs.z_vals.channels = 4
+        for k in ("initial", "end"):
+            if k in it:
+                del it[k]
+        it.use_dataset_bounds = True
+    elif variant == "outward_facing":  # immersive_*.yaml / bom_*.yaml
+        it.outward_facing = True
+    elif variant == "global_color":  # catacaustics_z_plane.yaml:77-100,148: per-ray scale / shift after compositing
+        outs = pred.outputs
+        for a, b in (("color_scale", "color_scale_global"), ("color_shift", "color_shift_global")):
+            items = [(b if k == a else k, v) for k, v in outs.items()]
+            for k in list(outs.keys()):
+                del outs[k]
+            for k, v in items:
+                outs[k] = v
+        f = emb.extract_fields.fields
+        emb.extract_fields.fields = [{"color_scale": "color_scale_global", "color_shift": "color_shift_global"}.get(k, k) for k in f]
+    elif variant == "both_color":  # per-sample and per-ray heads together (immersive_*.yaml field lists)
+        outs = pred.outputs
+        outs["color_scale_global"] = copy.deepcopy(outs["color_scale"])
+        outs["color_shift_global"] = copy.deepcopy(outs["color_shift"])
+        emb.extract_fields.fields = list(emb.extract_fields.fields) + ["color_scale_global", "color_shift_global"]
+    else:
+        raise ValueError(f"unknown variant {variant}")

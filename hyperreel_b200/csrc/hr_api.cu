@@ -174,9 +174,18 @@ int validate(const hr_config& c) {
   if (c.mlp_out != c.n_samples * c.head_stride) return fail("mlp_out %d != S*head_stride %d", c.mlp_out, c.n_samples * c.head_stride);
   if (c.off_z < 0) return fail("z_vals head is required");
   if (c.isect_type == HR_ISECT_Z_PLANE && c.n_z != 1) return fail("z_plane needs 1 z channel");
-  if (c.isect_type == HR_ISECT_SPHERE && c.n_z != 4) return fail("sphere needs 4 z channels");
-  if (c.isect_type != HR_ISECT_Z_PLANE && c.isect_type != HR_ISECT_SPHERE) return fail("unsupported intersect type %d", c.isect_type);
-  if (c.contract_type != HR_CONTRACT_NONE && c.contract_type != HR_CONTRACT_MIPNERF) return fail("unsupported contract type");
+  if ((c.isect_type == HR_ISECT_SPHERE || c.isect_type == HR_ISECT_CYLINDER) && c.n_z != 4) return fail("sphere / cylinder need 4 z channels");
+  if (c.isect_type != HR_ISECT_Z_PLANE && c.isect_type != HR_ISECT_SPHERE && c.isect_type != HR_ISECT_CYLINDER)
+    return fail("unsupported intersect type %d", c.isect_type);
+  if (c.contract_type != HR_CONTRACT_NONE && c.contract_type != HR_CONTRACT_MIPNERF && c.contract_type != HR_CONTRACT_AFFINE)
+    return fail("unsupported contract type");
+  if (c.contract_type == HR_CONTRACT_AFFINE) {
+    for (int i = 0; i < 3; ++i)
+      if (c.contract_affine_den[i] == 0.0f) return fail("affine contraction: zero extent on axis %d", i);
+    if (c.contract_dist_fac == 0.0f) return fail("affine contraction: zero distance factor");
+  }
+  if ((c.off_cscale_global >= 0) != (c.off_cshift_global >= 0)) return fail("color_scale_global and color_shift_global come together");
+  if (c.off_cscale_global + 3 > c.head_stride || c.off_cshift_global + 3 > c.head_stride) return fail("global colour heads out of range");
   if (c.use_flow && (c.off_flow < 0 || c.num_keyframes < 1 || c.num_frames < 1)) return fail("flow needs spatial_flow head and K,F");
   if (c.use_offset && c.off_offset < 0) return fail("point_offset needs point_offset head");
   if (c.use_color_scale_shift && (c.off_cscale < 0 || c.off_cshift < 0)) return fail("colour scale/shift heads missing");

@@ -79,6 +79,17 @@ __device__ __forceinline__ void contract_point(const hr_config& cfg, const Deriv
   }
 }
 
+// bbox / z_depth contraction of a point: (p - min) / den per axis (reference: nlf/contract.py:83-84, :109-110).
+__device__ __forceinline__ void contract_point_affine(const hr_config& cfg, float& x, float& y, float& z) {
+  x = __fdiv_rn(__fsub_rn(x, cfg.contract_affine_min[0]), cfg.contract_affine_den[0]);
+  y = __fdiv_rn(__fsub_rn(y, cfg.contract_affine_min[1]), cfg.contract_affine_den[1]);
+  z = __fdiv_rn(__fsub_rn(z, cfg.contract_affine_min[2]), cfg.contract_affine_den[2]);
+}
+// inverse contraction of a sample position (base.py:132-133): mipnerf (:143-158) or distance * fac (:77-78, :103-104)
+__device__ __forceinline__ float inv_contract_sample(const hr_config& cfg, const Derived& dv, float d) {
+  return (cfg.contract_type == HR_CONTRACT_AFFINE) ? __fmul_rn(d, cfg.contract_dist_fac) : inv_contract_distance(cfg, dv, d);
+}
+
 // Real SH basis, degree 2 (reference: utils/sh_utils.py:94-119).
 __device__ __forceinline__ void sh_basis9(float x, float y, float z, float (&Y)[9]) {
   const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
@@ -324,7 +335,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       if (cfg.isect_type == HR_ISECT_Z_PLANE) {
         float zr = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, hz[j][0])), one_m);
         float z = __fadd_rn(__fmul_rn(zr, cfg.z_scale), samp);
-        if (cfg.contract_samples) z = inv_contract_distance(cfg, dv, z);
+        if (cfg.contract_samples) z = inv_contract_sample(cfg, dv, z);
         float dzg = (fabsf(dz) < 1e-5f) ? 1e12f : dz;  // intersect_utils.py:135-142
         t = __fdiv_rn(__fsub_rn(z, oz), dzg);
       } else {
@@ -336,13 +347,21 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         float gy = __fadd_rn(__fmul_rn(zc[1], cfg.sphere_origin_scale), cfg.sphere_origin_initial[1]);
         float gz = __fadd_rn(__fmul_rn(zc[2], cfg.sphere_origin_scale), cfg.sphere_origin_initial[2]);
         float rad = __fadd_rn(__fmul_rn(zc[3], cfg.z_scale), samp);
-        if (cfg.contract_samples) rad = inv_contract_distance(cfg, dv, rad);
+        if (cfg.contract_samples) rad = inv_contract_sample(cfg, dv, rad);
         // primitive.py:420-438 + intersect_utils.py:45-84
         float sox = __fmul_rn(ox, gx), soy = __fmul_rn(oy, gy), soz = __fmul_rn(oz, gz);
         float sdx = __fmul_rn(dx, gx), sdy = __fmul_rn(dy, gy), sdz = __fmul_rn(dz, gz);
-        float oo = __fadd_rn(__fadd_rn(__fmul_rn(sox, sox), __fmul_rn(soy, soy)), __fmul_rn(soz, soz));
-        float dd = __fadd_rn(__fadd_rn(__fmul_rn(sdx, sdx), __fmul_rn(sdy, sdy)), __fmul_rn(sdz, sdz));
-        float od = __fadd_rn(__fadd_rn(__fmul_rn(sox, sdx), __fmul_rn(soy, sdy)), __fmul_rn(soz, sdz));
+        float oo, dd, od;
+        if (cfg.isect_type == HR_ISECT_CYLINDER) {
+          // IntersectCylinderOld (primitive.py:181-250) + intersect_cylinder (intersect_utils.py:86-125): x and z only
+          oo = __fadd_rn(__fmul_rn(sox, sox), __fmul_rn(soz, soz));
+          dd = __fadd_rn(__fmul_rn(sdx, sdx), __fmul_rn(sdz, sdz));
+          od = __fadd_rn(__fmul_rn(sox, sdx), __fmul_rn(soz, sdz));
+        } else {
+          oo = __fadd_rn(__fadd_rn(__fmul_rn(sox, sox), __fmul_rn(soy, soy)), __fmul_rn(soz, soz));
+          dd = __fadd_rn(__fadd_rn(__fmul_rn(sdx, sdx), __fmul_rn(sdy, sdy)), __fmul_rn(sdz, sdz));
+          od = __fadd_rn(__fadd_rn(__fmul_rn(sox, sdx), __fmul_rn(soy, sdy)), __fmul_rn(soz, sdz));
+        }
         float a = dd, b = __fmul_rn(2.0f, od), c = __fsub_rn(oo, __fmul_rn(rad, rad));
         float disc = __fsub_rn(__fmul_rn(b, b), __fmul_rn(__fmul_rn(4.0f, a), c));
         disc = (disc < 0.0f) ? 0.0f : disc;
@@ -375,6 +394,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     bool valid[SPL];
     float cocx = ox, cocy = oy, cocz = oz;
     if (cfg.contract_type == HR_CONTRACT_MIPNERF) contract_point(cfg, dv, cocx, cocy, cocz);
+    else if (cfg.contract_type == HR_CONTRACT_AFFINE) contract_point_affine(cfg, cocx, cocy, cocz);
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
       const int s = lane + 32 * j;
@@ -384,8 +404,9 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       float px = __fadd_rn(ox, __fmul_rn(dx, t));  // base.py:226
       float py = __fadd_rn(oy, __fmul_rn(dy, t));
       float pz = __fadd_rn(oz, __fmul_rn(dz, t));
-      if (cfg.contract_type == HR_CONTRACT_MIPNERF) {  // base.py:242-246, contract.py:43-50
-        contract_point(cfg, dv, px, py, pz);
+      if (cfg.contract_type != HR_CONTRACT_NONE) {  // base.py:242-246, contract.py:43-50
+        if (cfg.contract_type == HR_CONTRACT_MIPNERF) contract_point(cfg, dv, px, py, pz);
+        else contract_point_affine(cfg, px, py, pz);
         float ex = __fsub_rn(px, cocx), ey = __fsub_rn(py, cocy), ez = __fsub_rn(pz, cocz);
         t = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
         if (zero) t = 0.0f;
@@ -605,6 +626,12 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     if (lane < 3) {
       float v = accq + ((lane == 0) ? accB[0] : ((lane == 1) ? accB[1] : accB[2]));
       if (cfg.white_bg && !cfg.black_bg) v = v + (1.0f - accw);
+      if (cfg.off_cscale_global >= 0) {
+        // scale_shift_color_one (utils/tensorf_utils.py:275-281): the heads of sample 0 (MLP order) act on the pixel
+        const float gs = apply_act(cfg.act_cscale_global, __ldg(hrow + (long long)(cfg.off_cscale_global + lane) * S));
+        const float gb = apply_act(cfg.act_cshift_global, __ldg(hrow + (long long)(cfg.off_cshift_global + lane) * S));
+        v = __fadd_rn(__fmul_rn(v, __fadd_rn(gs, 1.0f)), gb);
+      }
       if (cfg.clamp_output) v = fminf(fmaxf(v, 0.0f), 1.0f);
       if (rgb8_out != nullptr) {
         // to8b (utils/__init__.py:47): (255 * clip(x, 0, 1)).astype(uint8) -- truncation

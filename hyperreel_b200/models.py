@@ -250,9 +250,17 @@ class LightfieldModel(nn.Module):
 
         P.on_device = 1
         net = self.embedding_model.embeddings[0].net
+        perm = list(self.sig.in_perm)
+        permuted = perm != list(range(len(perm)))
         for i, layer in enumerate(net.layers):
             lin = layer[0] if isinstance(layer, nn.Sequential) else layer
-            P.mlp_weight[i] = dptr(lin.weight)
+            w = lin.weight
+            if permuted and (i == 0 or i == self.sig.cfg.mlp_skip):
+                # BasicPE column order -> the kernels' per-band order (Signature.in_perm); the hidden part of the skip
+                # layer's input (cat([input, hidden]), mlp.py:167-168) keeps its place
+                cols = torch.tensor(perm + list(range(len(perm), w.shape[1])), device=w.device)
+                w = w.detach().index_select(1, cols)
+            P.mlp_weight[i] = dptr(w)
             P.mlp_bias[i] = dptr(lin.bias)
         tn = self.color_model.net
         dplane, dsecond, aplane, asecond = tn.tables()

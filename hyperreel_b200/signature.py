@@ -68,7 +68,8 @@ def _contract_distance(distance: torch.Tensor, start_distance: float, end_distan
     return (distance / 2.0) * 2.0
 
 
-HEAD_ROLES = ("z_vals", "spatial_flow", "sigma", "point_sigma", "point_offset", "color_scale", "color_shift")
+HEAD_ROLES = ("z_vals", "spatial_flow", "sigma", "point_sigma", "point_offset", "color_scale", "color_shift",
+              "color_scale_global", "color_shift_global")
 
 
 @dataclass
@@ -81,6 +82,10 @@ class Signature:
     head_channels: List[int] = field(default_factory=list)
     mlp_layer_shapes: List[tuple] = field(default_factory=list)  # (out, in) per Linear
     dynamic: bool = False
+    # kernel feature k of the encoded input = reference feature in_perm[k] (identity unless a group uses BasicPE, whose
+    # [x | sin(d-major, f-minor) | cos(...)] order differs from WindowedPE's per-band order); applied to the input columns
+    # of the first and the skip layer at upload
+    in_perm: List[int] = field(default_factory=list)
 
     @property
     def c_in(self) -> int:
@@ -144,6 +149,7 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     max_end = 6
     groups = []
     mlp_in = 0
+    in_perm: List[int] = []
     for key in pred.params.keys():
         p = pred.params[key]
         g = L.hr_encode_group()
@@ -169,7 +175,19 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
         g.mom_mult = float(_get(p.param, "moment_multiplier", 1.0))
         pe = _get(p, "pe")
         g.n_freqs, g.exclude_identity, g.freq_mult, g.base_mult = 0, 0, 2.0, 1.0
-        if pe is not None:
+        if pe is not None and pe.type == "basic":
+            # BasicPE (pe.py:32-68): same values as a fully open WindowedPE, other column order (handled by in_perm)
+            g.n_freqs = int(pe.n_freqs)
+            g.freq_mult = float(_get(pe, "freq_multiplier", 2.0))
+            D, Fq, k0 = dims, g.n_freqs, mlp_in
+            for i in range(D):
+                in_perm.append(k0 + i)
+            for f in range(Fq):
+                for i in range(D):
+                    in_perm.append(k0 + D + i * Fq + f)            # sin(band f, dim i)
+                for i in range(D):
+                    in_perm.append(k0 + D + D * Fq + i * Fq + f)   # cos(band f, dim i)
+        elif pe is not None:
             if pe.type != "windowed":
                 raise UnsupportedPipeline(f"pe type '{pe.type}' is not on the fused path")
             # all windows must be open (pe.py:186-196): cur_iter past wait and past max_freq_iter
@@ -184,6 +202,9 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
             g.exclude_identity = int(bool(_get(pe, "exclude_identity", False)))
             g.freq_mult = float(_get(pe, "freq_multiplier", 2.0))
             g.base_mult = float(_get(pe, "base_multiplier", 1.0))
+        if not (pe is not None and pe.type == "basic"):
+            n_feat = dims * (2 * g.n_freqs + (0 if g.exclude_identity else 1))
+            in_perm.extend(range(mlp_in, mlp_in + n_feat))
         mlp_in += dims * (2 * g.n_freqs + (0 if g.exclude_identity else 1))
         groups.append(g)
     if len(groups) > L.HR_MAX_GROUPS:
@@ -238,7 +259,8 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
             raise UnsupportedPipeline(f"head '{nme}' is not on the fused path")
         offs[nme] = o
         o += ch
-    expect_ch = {"spatial_flow": 3, "sigma": 1, "point_sigma": 1, "point_offset": 3, "color_scale": 3, "color_shift": 3}
+    expect_ch = {"spatial_flow": 3, "sigma": 1, "point_sigma": 1, "point_offset": 3, "color_scale": 3, "color_shift": 3,
+                 "color_scale_global": 3, "color_shift_global": 3}
     for nme, ch in zip(head_names, head_channels):
         if nme in expect_ch and ch != expect_ch[nme]:
             raise UnsupportedPipeline(f"head '{nme}' must have {expect_ch[nme]} channels")
@@ -261,10 +283,13 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
               "num_samples_for_scale", "use_local_prediction", "flip_axes"):
         if k in it and it[k] not in (False, None, 1):
             raise UnsupportedPipeline(f"intersect option '{k}' is not on the fused path")
-    for k in ("use_disparity", "residual_z", "residual_distance", "normalize", "clamp", "forward_facing", "max_axis",
-              "outward_facing"):
+    for k in ("use_disparity", "residual_z", "residual_distance", "normalize", "clamp", "forward_facing", "max_axis"):
         if _get(it, k, False):
             raise UnsupportedPipeline(f"intersect option '{k}' is not on the fused path")
+    # `outward_facing` is read by sphere_new / cylinder_new / voxel_grid only (primitive.py:262,447; voxel.py:24): the
+    # primitives on the fused path ignore it, exactly like the reference classes they mirror
+    if _get(it, "outward_facing", False) and it.type not in ("z_plane", "sphere", "cylinder"):
+        raise UnsupportedPipeline("intersect option 'outward_facing' is not on the fused path for this primitive")
     if _get(isect, "rays_name", "rays") != "rays":
         raise UnsupportedPipeline("rays_name override")
     use_ds = bool(_get(it, "use_dataset_bounds", False))
@@ -272,7 +297,31 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     c.contract_type, c.contract_samples = L.CONTRACT_NONE, 0
     c.contract_start_radius = c.contract_start_distance = 1.0
     c.contract_end_radius = c.contract_end_distance = float("inf")
-    if contract is not None and contract.type != "identity":
+    c.contract_dist_fac = 1.0
+    for i in range(3):
+        c.contract_affine_min[i], c.contract_affine_den[i] = 0.0, 1.0
+    affine_fac = None
+    if contract is not None and contract.type in ("bbox", "z_depth"):
+        if "distance_activation" in contract or "stop_iters" in contract:
+            raise UnsupportedPipeline("contract distance_activation / stop_iters")
+        if contract.type == "bbox":  # BBoxContract (contract.py:65-84)
+            bmin = torch.tensor([float(v) for v in _get(contract, "bbox_min", [-1.0, -1.0, -1.0])])
+            bmax = torch.tensor([float(v) for v in _get(contract, "bbox_max", [1.0, 1.0, 1.0])])
+            affine_fac = torch.mean(torch.abs(bmax - bmin))
+            den = bmax - bmin
+        else:  # ZDepthContract (contract.py:87-110)
+            er = _get(contract, "contract_end_radius",
+                      ds["depth_range"][1] if _get(contract, "use_dataset_bounds", False) else float("inf"))
+            if not (float(er) < float("inf")):
+                raise UnsupportedPipeline("z_depth contraction without a finite end radius")
+            affine_fac = torch.tensor(float(er) / 2.0)
+            bmin, den = torch.zeros(3), torch.full((3,), float(er) / 2.0)
+        c.contract_type = L.CONTRACT_AFFINE
+        c.contract_samples = int(bool(_get(contract, "contract_samples", False)))
+        c.contract_dist_fac = float(affine_fac)
+        for i in range(3):
+            c.contract_affine_min[i], c.contract_affine_den[i] = float(bmin[i]), float(den[i])
+    elif contract is not None and contract.type != "identity":
         if contract.type != "mipnerf":
             raise UnsupportedPipeline(f"contract '{contract.type}' is not on the fused path")
         if "distance_activation" in contract or "stop_iters" in contract:
@@ -294,8 +343,8 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
             initial, end = torch.tensor(-ds["near"]), torch.tensor(-ds["far"])
         else:
             initial, end = torch.tensor(_get(it, "initial", 0.0)), torch.tensor(_get(it, "end", 1.0))
-    elif it.type == "sphere":
-        c.isect_type = L.ISECT_SPHERE
+    elif it.type in ("sphere", "cylinder"):  # IntersectSphereOld / IntersectCylinderOld share their setup
+        c.isect_type = L.ISECT_SPHERE if it.type == "sphere" else L.ISECT_CYLINDER
         if use_ds:  # primitive.py:371-376
             initial = torch.tensor(_get(it, "initial", ds["near"] * 1.5))
             end = torch.tensor(_get(it, "end", ds["far"] * 1.5))
@@ -307,8 +356,12 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
         c.sphere_origin_scale = float(_get(it, "origin_scale_factor", 0.0))
     else:
         raise UnsupportedPipeline(f"intersect '{it.type}' is not on the fused path")
+    if c.n_z != (1 if it.type == "z_plane" else 4):
+        raise UnsupportedPipeline(f"intersect '{it.type}' needs {1 if it.type == 'z_plane' else 4} z_vals channel(s), got {c.n_z}")
     initial, end = initial.float(), end.float()
-    if c.contract_samples:
+    if c.contract_samples and c.contract_type == L.CONTRACT_AFFINE:  # contract_distance = d / fac (contract.py:80-81,106-107)
+        initial, end = initial / affine_fac, end / affine_fac
+    elif c.contract_samples:
         initial = _contract_distance(initial, c.contract_start_distance, c.contract_end_distance)
         end = _contract_distance(end, c.contract_start_distance, c.contract_end_distance)
     if S > L.HR_MAX_SAMPLES:
@@ -366,8 +419,15 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
         raise UnsupportedPipeline("add_point_outputs must add viewdirs")
     if dynamic and (flow is None or not all(f in fields for f in ("base_times", "times", "time_offset")) or "times" not in extras):
         raise UnsupportedPipeline("dynamic colour net needs advect_points + time fields")
-    if "color_transform" in offs or "color_scale_global" in offs:
+    if "color_transform" in offs or "color_transform_global" in offs:
         raise UnsupportedPipeline("colour transform heads are not on the fused path")
+    # per-ray colour scale / shift after compositing (tensorf_dynamic.py:798-800): present iff extract_fields passes them
+    glob = [k in offs and k in fields for k in ("color_scale_global", "color_shift_global")]
+    if glob[0] != glob[1]:
+        raise UnsupportedPipeline("color_scale_global and color_shift_global must come together")
+    c.off_cscale_global = offs["color_scale_global"] if glob[0] else -1
+    c.off_cshift_global = offs["color_shift_global"] if glob[0] else -1
+    c.act_cscale_global, c.act_cshift_global = act_of("color_scale_global"), act_of("color_shift_global")
     c.use_color_scale_shift = int("color_scale" in offs and "color_scale" in fields and "color_shift" in offs and "color_shift" in fields)
     if ("color_scale" in offs and "color_scale" in fields) != ("color_shift" in offs and "color_shift" in fields):
         raise UnsupportedPipeline("color_scale and color_shift must come together")
@@ -403,4 +463,4 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     c.density_shift = float(_get(net, "density_shift", -10.0))
     c.clamp_output = 1
     return Signature(cfg=c, model_cfg=m, dataset=ds, head_names=head_names, head_channels=head_channels,
-                     mlp_layer_shapes=shapes, dynamic=dynamic)
+                     mlp_layer_shapes=shapes, dynamic=dynamic, in_perm=in_perm)

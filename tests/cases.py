@@ -27,6 +27,14 @@ CASES: Dict[str, dict] = {
     "donerf_s16": dict(builtin="donerf_sphere", over=dict(n_voxels=32 ** 3, z_channels=16), n=128, seed=5, gain=30.0),
     "plumbing_4096x4": dict(builtin="donerf_sphere", over=dict(n_voxels=64 ** 3, z_channels=4), n=4096, seed=6, gain=30.0),
     "shiny_tiny": dict(builtin="shiny_z_plane_tiny", over=dict(n_voxels=32 ** 3), n=256, seed=7, gain=30.0),
+    # SURVEY 8 f3 families (config variants of the built-ins, hyperreel_b200/configs.py:_apply_variant)
+    "technicolor_basic_pe": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, variant="basic_pe"), n=128, seed=8, gain=30.0),
+    "technicolor_bbox": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, variant="bbox"), n=128, seed=9, gain=30.0),
+    "technicolor_z_depth": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, variant="z_depth"), n=128, seed=10, gain=30.0),
+    "donerf_cylinder": dict(builtin="donerf_sphere", over=dict(n_voxels=32 ** 3, variant=["cylinder", "outward_facing"]), n=192, seed=11, gain=30.0),
+    "technicolor_global_color": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, variant="global_color"), n=128, seed=12, gain=30.0),
+    "technicolor_both_color": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, variant="both_color"), n=128, seed=13, gain=30.0),
+    "immersive_sphere_like": dict(builtin="neural_3d_z_plane", over=dict(n_voxels=32 ** 3, z_channels=32, variant=["sphere", "outward_facing"]), n=160, seed=14, gain=30.0),
 }
 
 

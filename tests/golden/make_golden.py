@@ -9,7 +9,7 @@ deterministic -- and the hash guards against drift), and the reference outputs:
 (nlf/nets/tensorf_dynamic.py:821-823) and the sample-net output of the first 64 rays (forward hook on
 ``BaseMLP``).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]
 """
 from __future__ import annotations
 
@@ -31,7 +31,10 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 def main():
     ref_shim.install()
     torch.set_num_threads(8)
+    only = sys.argv[1:]  # optional: regenerate just these cases
     for name in CASES:
+        if only and name not in only:
+            continue
         case = build_case(name)
         ref = ref_shim.build_reference(case.model_cfg_plain, case.dataset)
         missing, unexpected = ref.load_state_dict(case.state_dict, strict=False)

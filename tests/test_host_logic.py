@@ -108,7 +108,11 @@ def test_lowering_donerf_uses_dataset_bounds_and_sigma_for_offset():
 def test_unsupported_pipelines_raise():
     cfg, ds = hb.configs.get("technicolor_z_plane")
     bad = hb.to_cfg(hb.config.to_plain(cfg))
-    bad.embedding.embeddings.ray_intersect_0.intersect.type = "cylinder"
+    bad.embedding.embeddings.ray_intersect_0.intersect.type = "cylinder_new"
+    with pytest.raises(UnsupportedPipeline):
+        lower(bad, ds)
+    bad = hb.to_cfg(hb.config.to_plain(cfg))
+    bad.embedding.embeddings.ray_intersect_0.intersect.type = "cylinder"  # 4-channel primitive behind a 1-channel head
     with pytest.raises(UnsupportedPipeline):
         lower(bad, ds)
     bad = hb.to_cfg(hb.config.to_plain(cfg))
@@ -123,6 +127,62 @@ def test_unsupported_pipelines_raise():
     bad.embedding.embeddings.ray_prediction_0.params.ray.param.fn = "spherical"
     with pytest.raises(UnsupportedPipeline):
         lower(bad, ds)
+
+
+def test_lowering_of_the_f3_families():
+    """BasicPE (column permutation), bbox / z_depth contraction, cylinder primitive, outward_facing (ignored
+    by the old sphere / cylinder / z_plane classes, primitive.py:181-250,366-438), per-ray colour heads."""
+    cfg, ds = hb.configs.get("technicolor_z_plane", variant="basic_pe")
+    sig = lower(cfg, ds)
+    assert sig.in_perm == [0, 1, 2, 3, 4, 5, 7, 6, 8]  # [t, sin2t, cos2t, sin4t, cos4t] <- BasicPE [t, sin2t, sin4t, cos2t, cos4t]
+    cfg, ds = hb.configs.get("technicolor_z_plane", variant="bbox")
+    c = lower(cfg, ds).cfg
+    assert c.contract_type == L.CONTRACT_AFFINE and c.contract_samples == 1
+    assert list(c.contract_affine_min) == [-2.0, -2.0, 0.5] and list(c.contract_affine_den) == [4.0, 4.0, -3.0]
+    assert abs(c.contract_dist_fac - (4.0 + 4.0 + 3.0) / 3.0) < 1e-6
+    initial = float(cfg.embedding.embeddings.ray_intersect_0.intersect.initial)
+    assert abs(c.samples[0] - initial / c.contract_dist_fac) < 1e-6  # contract_distance(initial) (contract.py:80-81)
+    cfg, ds = hb.configs.get("technicolor_z_plane", variant="z_depth")
+    c = lower(cfg, ds).cfg
+    assert c.contract_type == L.CONTRACT_AFFINE and list(c.contract_affine_den) == [1.5, 1.5, 1.5] and c.contract_dist_fac == 1.5
+    cfg, ds = hb.configs.get("donerf_sphere", variant=["cylinder", "outward_facing"])
+    c = lower(cfg, ds).cfg
+    assert c.isect_type == L.ISECT_CYLINDER and c.n_z == 4
+    cfg, ds = hb.configs.get("technicolor_z_plane", variant="global_color")
+    c = lower(cfg, ds).cfg
+    assert c.use_color_scale_shift == 0 and c.off_cscale_global == 9 and c.off_cshift_global == 12
+    cfg, ds = hb.configs.get("technicolor_z_plane", variant="both_color")
+    c = lower(cfg, ds).cfg
+    assert c.use_color_scale_shift == 1 and c.off_cscale_global == 15 and c.head_stride == 21
+    cfg, ds = hb.configs.get("neural_3d_z_plane", variant=["sphere", "outward_facing"])
+    c = lower(cfg, ds).cfg
+    assert c.isect_type == L.ISECT_SPHERE and c.dynamic == 1 and c.contract_type == L.CONTRACT_MIPNERF
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/conf/experiment/model"), reason="reference checkout not present")
+def test_shipped_model_yamls_that_lower_to_the_fused_path():
+    """Coverage ledger over the reference's 51 shipped model YAMLs: these must lower (DESIGN.md section 7 lists why the
+    rest are rejected)."""
+    import glob
+    ds = {"num_keyframes": 12, "num_frames": 50, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y"}
+    ok = set()
+    for f in sorted(glob.glob("/root/reference/conf/experiment/model/*.yaml")):
+        try:
+            lower(hb.load_model_yaml(f), ds)
+            ok.add(os.path.basename(f)[:-5])
+        except (UnsupportedPipeline, TypeError):  # bom_z_plane.yaml is an empty file
+            pass
+    expected = {
+        "donerf_sphere", "donerf_cylinder", "donerf_cylinder_no_point", "donerf_cylinder_small", "llff_z_plane", "llff_z_plane_small",
+        "neural_3d_z_plane", "neural_3d_z_plane_world", "shiny_z_plane_no_point",
+        "shiny_z_plane_small", "shiny_z_plane_tiny", "spaces_z_plane", "spaces_z_plane_world", "stanford_z_plane",
+        "stanford_z_plane_mem", "stanford_z_plane_small", "technicolor_z_plane", "technicolor_z_plane_ff",
+        "technicolor_z_plane_mem", "technicolor_z_plane_small", "technicolor_z_plane_tiny", "technicolor_z_plane_large",
+        "technicolor_z_plane_world", "immersive_sphere", "immersive_sphere_test", "immersive_cylinder", "immersive_cylinder_pe",
+        "bom_cylinder", "catacaustics_z_plane", "catacaustics_cylinder",
+    }
+    assert len(ok) >= 30
+    assert expected <= ok, sorted(expected - ok)
 
 
 def test_epochs_to_iters_rewrite():
