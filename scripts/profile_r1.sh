@@ -1,0 +1,5 @@
+# ncu evidence for the bench command (run on the GPU box through gpurun; outputs under gpurun_out/)
+set -x
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1f.csv python bench.py --steps 2 --warmup 1 > gpurun_out/launches_r1f.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"render_kernel|mlp_tc2_kernel" -s 4 -c 2 -f -o gpurun_out/prof_r1f python bench.py --steps 2 --warmup 1 > gpurun_out/prof_r1f.log 2>&1
+ls -la gpurun_out/
