@@ -407,6 +407,22 @@ static void drop_host_graph(hr_handle* h) {
   h->pipe.g_rays = nullptr; h->pipe.g_rgb = nullptr; h->pipe.g_n = 0; h->pipe.g_chunk = 0;
 }
 
+// rays [n, c_in] -> heads scratch [n, mlp_out] (channel-major per ray)
+static int launch_sample_net(hr_handle* h, const float* rays, int64_t n, float* heads, cudaStream_t st) {
+  const hr_config& c = h->cfg;
+  cudaError_t e;
+  if (c.mlp_mode == HR_MLP_BF16X3_TC) {
+    if (!h->tc_ready) return fail("hr_render: tensor-core pack missing");
+    e = (h->tc.version == 2) ? hr::launch_mlp_tc2(c, h->tc, rays, heads, n, h->num_sms, st)
+                             : hr::launch_mlp_tc(c, h->tc, rays, heads, n, h->num_sms, st);
+  } else {
+    e = hr::launch_mlp_simt(c, h->simt, rays, heads, n, h->num_sms, st);
+  }
+  if (e != cudaSuccess) return fail("sample-net launch failed: %s", cudaGetErrorString(e));
+  h->launches += 1;
+  return 0;
+}
+
 static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, float* mlp_out, const hr::StageOut* so,
                        void* workspace, int64_t ws_bytes, cudaStream_t st, unsigned char* rgb8 = nullptr) {
   if (!h) return fail("hr_render: null handle");
@@ -424,14 +440,8 @@ static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, f
     CK(cudaEventRecord(em.a, st));
   }
   cudaError_t e;
-  if (c.mlp_mode == HR_MLP_BF16X3_TC) {
-    if (!h->tc_ready) return fail("hr_render: tensor-core pack missing");
-    e = (h->tc.version == 2) ? hr::launch_mlp_tc2(c, h->tc, rays, heads, n, h->num_sms, st)
-                             : hr::launch_mlp_tc(c, h->tc, rays, heads, n, h->num_sms, st);
-  } else {
-    e = hr::launch_mlp_simt(c, h->simt, rays, heads, n, h->num_sms, st);
-  }
-  if (e != cudaSuccess) return fail("sample-net launch failed: %s", cudaGetErrorString(e));
+  int rc0 = launch_sample_net(h, rays, n, heads, st);
+  if (rc0) return rc0;
   if (timing) { CK(cudaEventRecord(em.b, st)); CK(cudaEventRecord(er.a, st)); }
   e = hr::launch_render(c, h->dv, h->tabs, rays, heads, rgb, n, so, h->num_sms, st, rgb8);
   if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
@@ -440,7 +450,7 @@ static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, f
     h->ev_mlp.push_back(em);
     h->ev_render.push_back(er);
   }
-  h->launches += 2;
+  h->launches += 1;
   if (mlp_out) {
     unpermute_heads<<<grid_for(n * (long long)c.mlp_out), 256, 0, st>>>(heads, mlp_out, n, c.n_samples, c.head_stride);
     e = cudaGetLastError();
@@ -530,12 +540,27 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
   if (!rays_host || !rgb_host) return fail("hr_render_host: null buffer");
   CK(cudaSetDevice(h->device));
   const hr_config& c = h->cfg;
-  // default chunk: one full wave of 128-ray tiles of the tensor-core sample net (148 x 128 = 18 944 rays on B200), so
-  // splitting a batch for copy/compute overlap adds no partially filled wave; 32 768 for the CUDA-core net
-  if (chunk <= 0) chunk = (c.mlp_mode == HR_MLP_BF16X3_TC) ? (int64_t)h->num_sms * 128 : 32768;
-  if (chunk > n_rays) chunk = n_rays;
   HostPipe& P = h->pipe;
-  if (P.chunk < chunk) {
+  const int64_t wave = (int64_t)h->num_sms * 128;  // one full wave of 128-ray tiles of the tensor-core sample net
+  // Default (chunk <= 0), tensor-core net, batches of a few waves: the "wave split" pipeline below.  Otherwise chunks of
+  // `chunk` rays (default: whole waves for the tensor-core net, 32 768 rays for the CUDA-core net) on three streams.
+  static const int allow_split = getenv("HR_HOST_SPLIT") ? atoi(getenv("HR_HOST_SPLIT")) : 1;
+  const bool whole = chunk <= 0 && c.mlp_mode == HR_MLP_BF16X3_TC && n_rays <= 16 * wave;  // the batch stays whole on the device
+  const float* rays_dev_view = nullptr;
+  static const int allow_zero_copy = getenv("HR_HOST_ZERO_COPY") ? atoi(getenv("HR_HOST_ZERO_COPY")) : 1;
+  if (allow_zero_copy && whole && h->tc_ready && h->tc.version == 2 && !h->timing) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, rays_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr)
+      rays_dev_view = (const float*)pa.devicePointer;
+    else
+      cudaGetLastError();  // pageable memory: not an error, just not device-addressable
+  }
+  const bool zero_copy = rays_dev_view != nullptr;
+  const bool split = !zero_copy && allow_split && whole && n_rays > wave;
+  if (chunk <= 0) chunk = (c.mlp_mode == HR_MLP_BF16X3_TC) ? wave : 32768;
+  if (chunk > n_rays) chunk = n_rays;
+  const int64_t alloc = (split || zero_copy) ? n_rays : chunk;  // rays per device slot
+  if (P.chunk < alloc) {
     drop_host_graph(h);
     for (int i = 0; i < 3; ++i) {
       if (P.d_rays[i]) cudaFree(P.d_rays[i]);
@@ -544,16 +569,21 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
       P.d_rays[i] = P.d_rgb[i] = nullptr; P.d_ws[i] = nullptr;
       if (!P.streams[i]) CK(cudaStreamCreateWithFlags(&P.streams[i], cudaStreamNonBlocking));
     }
-    P.ws_bytes = hr_workspace_bytes(h, chunk);
+    P.ws_bytes = hr_workspace_bytes(h, alloc);
     for (int i = 0; i < 3; ++i) {
-      CK(cudaMalloc((void**)&P.d_rays[i], (size_t)chunk * 8 * sizeof(float)));
-      CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)chunk * 3 * sizeof(float)));
+      CK(cudaMalloc((void**)&P.d_rays[i], (size_t)alloc * 8 * sizeof(float)));
+      CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)alloc * 3 * sizeof(float)));
       CK(cudaMalloc(&P.d_ws[i], (size_t)P.ws_bytes));
     }
-    P.chunk = chunk;
+    P.chunk = alloc;
   }
-  // The pipeline of one call: chunk i runs H2D -> sample net -> render -> D2H on stream i % 3.
-  auto enqueue = [&]() -> int {
+  if (!P.fork_ev) {
+    CK(cudaEventCreateWithFlags(&P.fork_ev, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) CK(cudaEventCreateWithFlags(&P.join_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&P.dep_ev[i], cudaEventDisableTiming));
+  }
+  // Chunked pipeline: chunk i runs H2D -> sample net -> render -> D2H on stream i % 3.
+  auto enqueue_chunks = [&]() -> int {
     int slot = 0;
     for (int64_t off = 0; off < n_rays; off += chunk, slot = (slot + 1) % 3) {
       int64_t m = (n_rays - off < chunk) ? (n_rays - off) : chunk;
@@ -565,17 +595,81 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
     }
     return 0;
   };
+  // Wave-split pipeline: splitting a batch into independent chunks costs one cold sample-net launch and one render tail
+  // per chunk, which eats what the copy overlap wins (measured: 0.404 ms unsplit vs 0.410 ms in four chunks).  Instead the
+  // batch stays whole on the device and only the edges are split:
+  //   copy-in  (stream 1): rays of the first tile wave, then the rest          -> events A, B
+  //   compute  (stream 0): sample net on the first wave after A, on the rest after B (together exactly the waves of the
+  //                        unsplit batch), then the render kernel in four pieces -> events R0..R3
+  //   copy-out (stream 2): rgb of piece j after Rj
+  // so only the first wave's H2D and the last piece's D2H are exposed.
+  auto enqueue_split = [&]() -> int {
+    cudaStream_t s0 = P.streams[0], s1 = P.streams[1], s2 = P.streams[2];
+    float* d_rays = P.d_rays[0];
+    float* d_rgb = P.d_rgb[0];
+    float* heads = (float*)P.d_ws[0];
+    const int64_t nA = wave, nB = n_rays - wave;
+    CK(cudaMemcpyAsync(d_rays, rays_host, (size_t)nA * c.c_in * sizeof(float), cudaMemcpyHostToDevice, s1));
+    CK(cudaEventRecord(P.dep_ev[0], s1));
+    CK(cudaMemcpyAsync(d_rays + nA * c.c_in, rays_host + nA * c.c_in, (size_t)nB * c.c_in * sizeof(float), cudaMemcpyHostToDevice, s1));
+    CK(cudaEventRecord(P.dep_ev[1], s1));
+    CK(cudaStreamWaitEvent(s0, P.dep_ev[0], 0));
+    int rc = launch_sample_net(h, d_rays, nA, heads, s0);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(s0, P.dep_ev[1], 0));
+    rc = launch_sample_net(h, d_rays + nA * c.c_in, nB, heads + nA * (int64_t)c.mlp_out, s0);
+    if (rc) return rc;
+    const int pieces = 4;
+    const int64_t per = ((n_rays + pieces - 1) / pieces + 255) / 256 * 256;
+    int j = 0;
+    for (int64_t off = 0; off < n_rays; off += per, ++j) {
+      const int64_t m = (n_rays - off < per) ? (n_rays - off) : per;
+      cudaError_t e = hr::launch_render(c, h->dv, h->tabs, d_rays + off * c.c_in, heads + off * (int64_t)c.mlp_out, d_rgb + off * 3, m,
+                                        nullptr, h->num_sms, s0, nullptr);
+      if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
+      h->launches += 1;
+      CK(cudaEventRecord(P.dep_ev[2 + j], s0));
+      CK(cudaStreamWaitEvent(s2, P.dep_ev[2 + j], 0));
+      CK(cudaMemcpyAsync(rgb_host + off * 3, d_rgb + off * 3, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, s2));
+    }
+    return 0;
+  };
+  // Zero-copy input: when the caller's rays are pinned (device-addressable) host memory and the second tensor-core layout
+  // is in use, the sample net reads them straight over PCIe -- its two encoder warps work one tile ahead of the tensor
+  // pipe, so the transfer hides under the math without splitting any launch -- and leaves a device copy for the render
+  // kernel.  The render kernel then runs in two pieces so that half of the D2H overlaps it.
+  auto enqueue_zero_copy = [&]() -> int {
+    cudaStream_t s0 = P.streams[0], s2 = P.streams[2];
+    float* d_rays = P.d_rays[0];
+    float* d_rgb = P.d_rgb[0];
+    float* heads = (float*)P.d_ws[0];
+    cudaError_t e = hr::launch_mlp_tc2(c, h->tc, rays_dev_view, heads, n_rays, h->num_sms, s0, d_rays);
+    if (e != cudaSuccess) return fail("sample-net launch failed: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    const int pieces = 2;
+    const int64_t per = ((n_rays + pieces - 1) / pieces + 255) / 256 * 256;
+    int j = 0;
+    for (int64_t off = 0; off < n_rays; off += per, ++j) {
+      const int64_t m = (n_rays - off < per) ? (n_rays - off) : per;
+      e = hr::launch_render(c, h->dv, h->tabs, d_rays + off * c.c_in, heads + off * (int64_t)c.mlp_out, d_rgb + off * 3, m, nullptr,
+                            h->num_sms, s0, nullptr);
+      if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
+      h->launches += 1;
+      CK(cudaEventRecord(P.dep_ev[2 + j], s0));
+      CK(cudaStreamWaitEvent(s2, P.dep_ev[2 + j], 0));
+      CK(cudaMemcpyAsync(rgb_host + off * 3, d_rgb + off * 3, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, s2));
+    }
+    return 0;
+  };
+  auto enqueue = [&]() -> int { return zero_copy ? enqueue_zero_copy() : (split ? enqueue_split() : enqueue_chunks()); };
   static const int use_graph = getenv("HR_HOST_GRAPH") ? atoi(getenv("HR_HOST_GRAPH")) : 1;
   const int64_t n_chunks = (n_rays + chunk - 1) / chunk;
-  if (use_graph && !h->timing && n_chunks > 1) {
-    // Launch-bound when issued call by call (5 driver calls per chunk against ~75 us of GPU work per chunk): capture the
-    // whole multi-stream pipeline once per (buffers, size) signature and replay it with a single graph launch.
-    if (!(P.graph && P.g_rays == rays_host && P.g_rgb == rgb_host && P.g_n == n_rays && P.g_chunk == chunk)) {
+  const int64_t key_chunk = zero_copy ? -2 : (split ? -1 : chunk);
+  if (use_graph && !h->timing && (zero_copy || split || n_chunks > 1)) {
+    // Launch-bound when issued call by call: capture the whole multi-stream pipeline once per (buffers, size) signature
+    // and replay it with a single graph launch.
+    if (!(P.graph && P.g_rays == rays_host && P.g_rgb == rgb_host && P.g_n == n_rays && P.g_chunk == key_chunk)) {
       drop_host_graph(h);
-      if (!P.fork_ev) {
-        CK(cudaEventCreateWithFlags(&P.fork_ev, cudaEventDisableTiming));
-        for (int i = 0; i < 3; ++i) CK(cudaEventCreateWithFlags(&P.join_ev[i], cudaEventDisableTiming));
-      }
       const int64_t launches_before = h->launches;
       cudaGraph_t g = nullptr;
       CK(cudaStreamBeginCapture(P.streams[0], cudaStreamCaptureModeRelaxed));
@@ -587,16 +681,17 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
         cudaStreamWaitEvent(P.streams[0], P.join_ev[i], 0);
       }
       cudaError_t ce = cudaStreamEndCapture(P.streams[0], &g);
+      P.g_launches = h->launches - launches_before;
       h->launches = launches_before;  // capture enqueued nothing; the replay below is what runs
       if (rc) { if (g) cudaGraphDestroy(g); return rc; }
       if (ce != cudaSuccess) return fail("hr_render_host: graph capture failed: %s", cudaGetErrorString(ce));
       ce = cudaGraphInstantiate(&P.graph, g, 0);
       cudaGraphDestroy(g);
       if (ce != cudaSuccess) { P.graph = nullptr; return fail("hr_render_host: graph instantiate failed: %s", cudaGetErrorString(ce)); }
-      P.g_rays = rays_host; P.g_rgb = rgb_host; P.g_n = n_rays; P.g_chunk = chunk;
+      P.g_rays = rays_host; P.g_rgb = rgb_host; P.g_n = n_rays; P.g_chunk = key_chunk;
     }
     CK(cudaGraphLaunch(P.graph, P.streams[0]));
-    h->launches += 2 * n_chunks;
+    h->launches += P.g_launches;
     CK(cudaStreamSynchronize(P.streams[0]));
     return 0;
   }
@@ -654,6 +749,8 @@ int hr_destroy(hr_handle* h) {
     if (i == 0) {
       drop_host_graph(h);
       if (h->pipe.fork_ev) cudaEventDestroy(h->pipe.fork_ev);
+      for (int k = 0; k < 8; ++k)
+        if (h->pipe.dep_ev[k]) cudaEventDestroy(h->pipe.dep_ev[k]);
     }
     if (h->pipe.join_ev[i]) cudaEventDestroy(h->pipe.join_ev[i]);
     if (h->pipe.d_rays[i]) cudaFree(h->pipe.d_rays[i]);

@@ -23,8 +23,9 @@ struct HostPipe {
   cudaGraphExec_t graph = nullptr;
   const void* g_rays = nullptr;
   void* g_rgb = nullptr;
-  int64_t g_n = 0, g_chunk = 0;
+  int64_t g_n = 0, g_chunk = 0, g_launches = 0;
   cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t dep_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // wave-split pipeline edges
 };
 
 struct hr_handle {

@@ -49,8 +49,9 @@ cudaError_t launch_mlp_simt(const hr_config& cfg, const MlpSimtPack& pk, const f
 
 cudaError_t launch_mlp_tc(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
                           int num_sms, cudaStream_t stream);
+// rays may point to pinned host memory (read once, by the encoder warps); rays_copy (optional) receives a device copy
 cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
-                           int num_sms, cudaStream_t stream);
+                           int num_sms, cudaStream_t stream, float* rays_copy = nullptr);
 }  // namespace hr
 
 struct hr_handle;

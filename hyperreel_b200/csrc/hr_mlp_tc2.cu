@@ -88,7 +88,7 @@ __device__ __forceinline__ uint32_t ks_slot(int row, int kg) { return (uint32_t)
 __global__ void __launch_bounds__(tc2::NTHREADS, 1)
 mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ MlpTcPack pk, const float* __restrict__ rays,
                float* __restrict__ heads, long long n_rays, unsigned long long* trace,
-               const __grid_constant__ CUtensorMap heads_map, int use_tma_store) {
+               const __grid_constant__ CUtensorMap heads_map, int use_tma_store, float* __restrict__ rays_copy) {
   using namespace tc2;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -295,6 +295,7 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
     // bf16 hi / lo slot of the UMMA-layout operand.  Runs one tile ahead of the tensor pipe: buffer b is released by the
     // issuer (BAR_XFREE) once the previous tile's readers have retired.
     const int et = (warp - (EPI_WARPS + 2)) * 32 + lane;  // 0 .. 63
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(rays) | reinterpret_cast<uintptr_t>(rays_copy)) & 15) == 0;
     for (long long j = 0; j < n_iters; ++j) {
       const uint32_t xb = (uint32_t)(j & 1);
       if (j >= 1) mbar_wait(bar(BAR_XFREE + xb), (uint32_t)(((j - 1) >> 1) & 1));
@@ -310,7 +311,24 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
         };
         const long long ray = tile * BM + r;
         if (ray < n_rays) {
-          encode_ray_features(cfg, rays + ray * cfg.c_in, 0, 1, put);
+          // The ray is read exactly once, with vector loads: `rays` may be pinned host memory (zero-copy input of
+          // hr_render_host), in which case this warp's loads are the host->device transfer, one tile ahead of the math,
+          // and `rays_copy` receives the device copy the render kernel reads.
+          float rbuf[16];
+          const float* src = rays + ray * cfg.c_in;
+          if (cfg.c_in == 8 && vec_ok) {
+            const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+            rbuf[0] = a.x; rbuf[1] = a.y; rbuf[2] = a.z; rbuf[3] = a.w; rbuf[4] = b.x; rbuf[5] = b.y; rbuf[6] = b.z; rbuf[7] = b.w;
+            if (rays_copy != nullptr) {
+              float4* dst = reinterpret_cast<float4*>(rays_copy + ray * 8);
+              dst[0] = a; dst[1] = b;
+            }
+          } else {
+            for (int i = 0; i < cfg.c_in; ++i) rbuf[i] = src[i];
+            if (rays_copy != nullptr)
+              for (int i = 0; i < cfg.c_in; ++i) rays_copy[ray * cfg.c_in + i] = rbuf[i];
+          }
+          encode_ray_features(cfg, rbuf, 0, 1, put);
         } else {
           for (int k = 0; k < cfg.mlp_in; ++k) put(k, 0.0f);  // masked row: defined (never stored) values
         }
@@ -534,7 +552,7 @@ int pack_mlp_tc2(hr_handle* h, const hr_params*, const float* const* w_dev, cons
 }
 
 cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n, int num_sms,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, float* rays_copy) {
   unsigned long long* trace = nullptr;
   const bool want_trace = getenv("HR_TC_TRACE") != nullptr;
   if (want_trace) {
@@ -555,7 +573,7 @@ cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, const floa
   CUtensorMap hmap;
   static const int want_tma = getenv("HR_TC_TMA_STORE") ? atoi(getenv("HR_TC_TMA_STORE")) : 1;
   const int use_tma = (want_tma && make_heads_map(&hmap, heads, cfg.mlp_out, n)) ? 1 : 0;
-  mlp_tc2_kernel<<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, stream>>>(cfg, pk, rays, heads, n, trace, hmap, use_tma);
+  mlp_tc2_kernel<<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, stream>>>(cfg, pk, rays, heads, n, trace, hmap, use_tma, rays_copy);
   cudaError_t le = cudaGetLastError();
   if (want_trace) {
     unsigned long long hbuf[1024];

@@ -63,6 +63,7 @@ class LightfieldModel(nn.Module):
         self._lib = L.load_library()  # raises if the CUDA library is missing -- no fallback
         self._handle = C.c_void_p()
         self._uploaded_version = None
+        self._version_tensors = None
         self._device_index: Optional[int] = None
         self._ws: Optional[torch.Tensor] = None
 
@@ -194,6 +195,7 @@ class LightfieldModel(nn.Module):
     def mark_dirty(self):
         """Call after mutating parameters in place (optimiser step, manual edits) so the next render re-packs."""
         self._uploaded_version = None
+        self._version_tensors = None
 
     def _check_rays(self, rays):
         if not rays.is_cuda:
@@ -212,10 +214,14 @@ class LightfieldModel(nn.Module):
         return self._ws
 
     def _param_version(self):
-        # version counters + storage addresses only: no device synchronisation on the per-call path
+        # version counters + storage addresses only: no device synchronisation and no module-tree walk on the per-call
+        # path (the Parameter / buffer objects are cached; mark_dirty() drops the cache for code that replaces them)
         net = self.color_model.net
-        return tuple((p._version, p.data_ptr()) for p in self.parameters()) + tuple(
-            (b._version, b.data_ptr()) for b in (net.aabb, net.gridSize))
+        sv = getattr(net, "struct_version", 0)
+        ts = self._version_tensors
+        if ts is None or ts[0] != sv:  # init_svd_volume (a resized grid) replaced the table Parameters
+            ts = self._version_tensors = (sv, list(self.parameters()) + [net.aabb, net.gridSize])
+        return tuple([(t._version, t.data_ptr()) for t in ts[1]])
 
     def _ensure_uploaded(self, dev: torch.device):
         idx = dev.index if dev.index is not None else torch.cuda.current_device()

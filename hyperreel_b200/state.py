@@ -94,6 +94,7 @@ class _Tensorf(nn.Module):
         setattr(self, names[1], nn.ParameterList(d2))
         setattr(self, names[2], nn.ParameterList(ap))
         setattr(self, names[3], nn.ParameterList(a2))
+        self.struct_version = getattr(self, "struct_version", 0) + 1  # new Parameter objects: caches keyed on them are stale
 
     def update_stepSize(self, gridSize):
         self.gridSize = torch.as_tensor(gridSize, dtype=torch.long)

@@ -108,6 +108,27 @@ def test_host_buffer_entry_point_matches_device_path():
     assert torch.equal(host, dev)
 
 
+def test_host_entry_point_whole_batch_pipelines_match_device_path():
+    """Default chunking with the tensor-core net (hr_render_host keeps the batch whole on the device):
+    pinned rays  -> zero-copy input (the sample net's encoder warps read host memory, render in two pieces);
+    pageable rays -> wave split (H2D split at the first 148 x 128-ray wave, sample net in two launches, render in four)."""
+    case = build_case("technicolor_trained", n=148 * 128 + 3000)
+    render = make_render(case, mlp_mode="bf16x3")
+    dev = render(case.rays.cuda())["rgb"].cpu()
+    for pinned in (True, False):
+        rays = case.rays.clone()
+        out = torch.empty((case.rays.shape[0], 3), dtype=torch.float32)
+        if pinned:
+            rays, out = rays.pin_memory(), out.pin_memory()
+        for _ in range(2):  # capture, then replay
+            out.zero_()
+            render.model.render_host(rays, out)
+            assert torch.equal(out, dev), f"pinned={pinned}"
+    # a batch smaller than one wave through the zero-copy path
+    small = case.rays[:777].clone().pin_memory()
+    assert torch.equal(render.model.render_host(small), dev[:777])
+
+
 def test_host_entry_point_graph_replay_tracks_buffers_and_reupload():
     """hr_render_host replays a captured CUDA graph while (buffers, size, chunk) repeat: new ray values in the same
     pinned buffer and re-uploaded parameters must both show up in the replayed result."""
