@@ -240,6 +240,22 @@ def _apply_variant(cfg: Cfg, variant: str) -> None:
             if k in it:
                 del it[k]
         it.use_dataset_bounds = True
+    elif variant == "sphere_new":  # immersive_sphere_new.yaml:153-172 / bom_sphere.yaml:149-163
+        if it.type not in ("z_plane", "sphere"):
+            raise ValueError("the sphere_new variant starts from a z_plane or sphere pipeline")
+        it.type = "sphere_new"
+        it.origin_scale_factor = 1.0
+        it.resize_scale_factor = 1.0
+        pred.outputs.z_vals.channels = 8
+        for k in ("initial", "end"):
+            if k in it:
+                del it[k]
+        it.use_dataset_bounds = True
+    elif variant == "scale_mask":  # shiny_z_plane.yaml:143 (num_samples_for_scale), stanford_llff_z_plane.yaml:142-143 (mask)
+        it.num_samples_for_scale = 2 * int(emb.ray_intersect_0.z_channels)
+        it.mask = to_cfg({"stop_iters": -1})
+    elif variant == "z_scale":
+        it.z_scale = 0.05
     elif variant == "outward_facing":  # immersive_*.yaml / bom_*.yaml
         it.outward_facing = True
     elif variant == "global_color":  # catacaustics_z_plane.yaml:77-100,148: per-ray scale / shift after compositing

@@ -175,8 +175,8 @@ int validate(const hr_config& c) {
   if (c.off_z < 0) return fail("z_vals head is required");
   if (c.isect_type == HR_ISECT_Z_PLANE && c.n_z != 1) return fail("z_plane needs 1 z channel");
   if ((c.isect_type == HR_ISECT_SPHERE || c.isect_type == HR_ISECT_CYLINDER) && c.n_z != 4) return fail("sphere / cylinder need 4 z channels");
-  if (c.isect_type != HR_ISECT_Z_PLANE && c.isect_type != HR_ISECT_SPHERE && c.isect_type != HR_ISECT_CYLINDER)
-    return fail("unsupported intersect type %d", c.isect_type);
+  if (c.isect_type == HR_ISECT_SPHERE_NEW && c.n_z != 8) return fail("sphere_new needs 8 z channels");
+  if (c.isect_type < HR_ISECT_Z_PLANE || c.isect_type > HR_ISECT_SPHERE_NEW) return fail("unsupported intersect type %d", c.isect_type);
   if (c.contract_type != HR_CONTRACT_NONE && c.contract_type != HR_CONTRACT_MIPNERF && c.contract_type != HR_CONTRACT_AFFINE)
     return fail("unsupported contract type");
   if (c.contract_type == HR_CONTRACT_AFFINE) {

@@ -338,6 +338,66 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         if (cfg.contract_samples) z = inv_contract_sample(cfg, dv, z);
         float dzg = (fabsf(dz) < 1e-5f) ? 1e12f : dz;  // intersect_utils.py:135-142
         t = __fdiv_rn(__fsub_rn(z, oz), dzg);
+      } else if (cfg.isect_type == HR_ISECT_SPHERE_NEW) {
+        // IntersectSphereNew (primitive.py:489-546): 8 channels per sample = origin 3, resize 3, offset 1, radius 1.  The
+        // last four are read here (the heads row sits in L1) so the other pipelines keep their register budget.
+        float zc[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) zc[c] = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, hz[j][c])), one_m);
+#pragma unroll
+        for (int c = 4; c < 8; ++c) {
+          const float raw = __ldg(hrow + (long long)(cfg.off_z + c) * S + (act ? s : 0));
+          zc[c] = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, raw)), one_m);
+        }
+        float org[3], rsz[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          org[c] = __fmul_rn(zc[c], cfg.sphere_origin_scale);                                                        // :489-491
+          rsz[c] = __fadd_rn(__fmul_rn(zc[3 + c], cfg.sphere_resize_scale), cfg.sphere_resize_initial[c]);           // :493-495
+        }
+        float roff = __fadd_rn(__fmul_rn(zc[6], cfg.z_scale), samp);  // :501-502, both through process_z_vals
+        float rad = __fadd_rn(__fmul_rn(zc[7], cfg.z_scale), samp);
+        if (cfg.contract_samples) { roff = inv_contract_sample(cfg, dv, roff); rad = inv_contract_sample(cfg, dv, rad); }
+        // transformed ray (:512-521)
+        const float rox = __fmul_rn(__fsub_rn(ox, org[0]), rsz[0]), roy = __fmul_rn(__fsub_rn(oy, org[1]), rsz[1]),
+                    roz = __fmul_rn(__fsub_rn(oz, org[2]), rsz[2]);
+        const float rdx = __fmul_rn(dx, rsz[0]), rdy = __fmul_rn(dy, rsz[1]), rdz = __fmul_rn(dz, rsz[2]);
+        const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rdx, rdx), __fmul_rn(rdy, rdy)), __fmul_rn(rdz, rdz)));
+        const float nd = fmaxf(nrm, 1e-12f);  // F.normalize
+        const float ux = __fdiv_rn(rdx, nd), uy = __fdiv_rn(rdy, nd), uz = __fdiv_rn(rdz, nd);
+        // intersect_sphere (intersect_utils.py:45-84)
+        float tq;
+        {
+          const float oo = __fadd_rn(__fadd_rn(__fmul_rn(rox, rox), __fmul_rn(roy, roy)), __fmul_rn(roz, roz));
+          const float dd = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz));
+          const float od = __fadd_rn(__fadd_rn(__fmul_rn(rox, ux), __fmul_rn(roy, uy)), __fmul_rn(roz, uz));
+          const float a = dd, b = __fmul_rn(2.0f, od), c = __fsub_rn(oo, __fmul_rn(rad, rad));
+          float disc = __fsub_rn(__fmul_rn(b, b), __fmul_rn(__fmul_rn(4.0f, a), c));
+          disc = (disc < 0.0f) ? 0.0f : disc;
+          const float sq = sqrtf(__fadd_rn(disc, 1e-8f));
+          const float a2 = __fmul_rn(2.0f, a);
+          float t1 = __fdiv_rn(__fadd_rn(-b, sq), a2);
+          float t2 = __fdiv_rn(__fsub_rn(-b, sq), a2);
+          if (disc <= 0.0f) { t1 = 0.0f; t2 = 0.0f; }
+          tq = ((t2 < 0.0f) || (rad < 0.0f)) ? t1 : t2;
+        }
+        // min_sphere_radius (intersect_utils.py:27-33) and pluecker_pos (param.py:297-307) normalise the direction again
+        const float n2 = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 1e-12f);
+        const float vx = __fdiv_rn(ux, n2), vy = __fdiv_rn(uy, n2), vz = __fdiv_rn(uz, n2);
+        const float mx = __fsub_rn(__fmul_rn(roy, vz), __fmul_rn(roz, vy));  // m = cross(o, v)
+        const float my = __fsub_rn(__fmul_rn(roz, vx), __fmul_rn(rox, vz));
+        const float mz = __fsub_rn(__fmul_rn(rox, vy), __fmul_rn(roy, vx));
+        const float bx = __fsub_rn(__fmul_rn(vy, mz), __fmul_rn(vz, my));    // base = cross(v, m)
+        const float by = __fsub_rn(__fmul_rn(vz, mx), __fmul_rn(vx, mz));
+        const float bz = __fsub_rn(__fmul_rn(vx, my), __fmul_rn(vy, mx));
+        const float min_radius = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)), __fmul_rn(bz, bz)));
+        const float ex = __fsub_rn(bx, rox), ey = __fsub_rn(by, roy), ez = __fsub_rn(bz, roz);
+        const float dotde = __fadd_rn(__fadd_rn(__fmul_rn(ux, ex), __fmul_rn(uy, ey)), __fmul_rn(uz, ez));
+        const float sgn = (dotde > 0.0f) ? 1.0f : ((dotde < 0.0f) ? -1.0f : 0.0f);
+        const float base_distance = __fmul_rn(sgn, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez))));
+        // recycle samples of spheres the ray misses (:534-538), then back to world distances (:541)
+        if (fabsf(rad) < __fadd_rn(min_radius, __fmul_rn(4.0f, cfg.z_scale))) tq = __fadd_rn(roff, base_distance);
+        t = __fdiv_rn(tq, __fadd_rn(nrm, 1e-5f));
       } else {
         float zc[4];
 #pragma unroll

@@ -11,14 +11,14 @@ import os
 import subprocess
 import threading
 
-HR_ABI_VERSION = 5
+HR_ABI_VERSION = 6
 HR_MAX_GROUPS = 4
 HR_MAX_LAYERS = 10
 HR_MAX_SAMPLES = 64
 
 ACT_IDENTITY, ACT_SIGMOID, ACT_TANH = 0, 1, 2
 PARAM_IDENTITY, PARAM_TWO_PLANE, PARAM_PLUECKER = 0, 1, 2
-ISECT_Z_PLANE, ISECT_SPHERE, ISECT_CYLINDER = 0, 1, 2
+ISECT_Z_PLANE, ISECT_SPHERE, ISECT_CYLINDER, ISECT_SPHERE_NEW = 0, 1, 2, 3
 CONTRACT_NONE, CONTRACT_MIPNERF, CONTRACT_AFFINE = 0, 1, 2
 SHADE_SH, SHADE_RGB = 0, 1
 DENSE_RELU, DENSE_SOFTPLUS, DENSE_RELU_ABS = 0, 1, 2
@@ -69,6 +69,7 @@ class hr_config(C.Structure):
         ("contract_affine_min", C.c_float * 3), ("contract_affine_den", C.c_float * 3), ("contract_dist_fac", C.c_float),
         ("off_cscale_global", C.c_int32), ("off_cshift_global", C.c_int32),
         ("act_cscale_global", hr_act), ("act_cshift_global", hr_act),
+        ("sphere_resize_scale", C.c_float), ("sphere_resize_initial", C.c_float * 3),
     ]
 
 

@@ -279,8 +279,7 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
 
     # ------------------------------------------------------------------ intersection (base.py:52-126, z.py, primitive.py)
     it = isect.intersect
-    for k in ("origin", "weight_fn", "sort_outputs", "mask", "dropout", "num_repeat", "z_scale",
-              "num_samples_for_scale", "use_local_prediction", "flip_axes"):
+    for k in ("origin", "weight_fn", "sort_outputs", "dropout", "num_repeat", "use_local_prediction", "flip_axes"):
         if k in it and it[k] not in (False, None, 1):
             raise UnsupportedPipeline(f"intersect option '{k}' is not on the fused path")
     for k in ("use_disparity", "residual_z", "residual_distance", "normalize", "clamp", "forward_facing", "max_axis"):
@@ -288,7 +287,7 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
             raise UnsupportedPipeline(f"intersect option '{k}' is not on the fused path")
     # `outward_facing` is read by sphere_new / cylinder_new / voxel_grid only (primitive.py:262,447; voxel.py:24): the
     # primitives on the fused path ignore it, exactly like the reference classes they mirror
-    if _get(it, "outward_facing", False) and it.type not in ("z_plane", "sphere", "cylinder"):
+    if it.type not in ("z_plane", "sphere", "cylinder", "sphere_new") and _get(it, "outward_facing", False):
         raise UnsupportedPipeline("intersect option 'outward_facing' is not on the fused path for this primitive")
     if _get(isect, "rays_name", "rays") != "rays":
         raise UnsupportedPipeline("rays_name override")
@@ -354,10 +353,26 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
         for i in range(3):
             c.sphere_origin_initial[i] = float(oi[i])
         c.sphere_origin_scale = float(_get(it, "origin_scale_factor", 0.0))
+    elif it.type == "sphere_new":  # IntersectSphereNew (primitive.py:440-487)
+        c.isect_type = L.ISECT_SPHERE_NEW
+        if use_ds:  # :446-452: outward_facing picks the sign of the first sphere
+            if _get(it, "outward_facing", False):
+                initial = torch.tensor(_get(it, "initial", ds["near"] * 1.5))
+            else:
+                initial = torch.tensor(_get(it, "initial", -ds["far"] * 1.5))
+            end = torch.tensor(_get(it, "end", ds["far"] * 1.5))
+        else:
+            initial, end = torch.tensor(_get(it, "initial", 0.0)), torch.tensor(_get(it, "end", 1.0))
+        c.sphere_origin_scale = float(_get(it, "origin_scale_factor", 0.0))
+        c.sphere_resize_scale = float(_get(it, "resize_scale_factor", 0.0))
+        ri = _get(it, "resize_initial", [1.0, 1.0, 1.0])
+        for i in range(3):
+            c.sphere_resize_initial[i] = float(ri[i])
     else:
         raise UnsupportedPipeline(f"intersect '{it.type}' is not on the fused path")
-    if c.n_z != (1 if it.type == "z_plane" else 4):
-        raise UnsupportedPipeline(f"intersect '{it.type}' needs {1 if it.type == 'z_plane' else 4} z_vals channel(s), got {c.n_z}")
+    need_z = {"z_plane": 1, "sphere_new": 8}.get(it.type, 4)
+    if c.n_z != need_z:
+        raise UnsupportedPipeline(f"intersect '{it.type}' needs {need_z} z_vals channel(s), got {c.n_z}")
     initial, end = initial.float(), end.float()
     if c.contract_samples and c.contract_type == L.CONTRACT_AFFINE:  # contract_distance = d / fac (contract.py:80-81,106-107)
         initial, end = initial / affine_fac, end / affine_fac
@@ -369,9 +384,21 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     samples = torch.linspace(float(initial), float(end), S)
     for i in range(S):
         c.samples[i] = float(samples[i])
-    c.z_scale = float(torch.abs(samples[1] - samples[0])) if S > 1 else 1.0
+    # z.py:58-71 (the primitives take cfg.z_scale or the sample spacing: primitive.py:211-219)
+    if "z_scale" in it:
+        c.z_scale = float(it.z_scale)
+    elif S > 1:
+        zs = torch.abs(samples[1] - samples[0])
+        if "num_samples_for_scale" in it and it.type == "z_plane":
+            zs = zs * (S / float(it.num_samples_for_scale))
+        c.z_scale = float(zs)
+    else:
+        c.z_scale = 1.0
     c.isect_near = float(_get(it, "near", ds["near"] if use_ds else 0.0))
     c.isect_far = float(_get(it, "far", float("inf")))
+    if "mask" in it and it.mask is not None and cur_iter > float(_get(it.mask, "stop_iters", float("inf"))):
+        # base.py:104-105,197-198: past mask.stop_iters nothing is masked (samples with t == 0 still drop out downstream)
+        c.isect_near, c.isect_far = float("-inf"), float("inf")
     c.isect_sort = int(bool(_get(it, "sort", False)))
     c.isect_act = resolve_activation(_get(it, "activation", "identity"), cur_iter)
     c.isect_use_sigma = int(bool(_get(it, "use_sigma", False)))

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HR_ABI_VERSION 5
+#define HR_ABI_VERSION 6
 
 #define HR_MAX_GROUPS 4   /* ray-parameterisation groups feeding the sample net (ray.py:235-263) */
 #define HR_MAX_LAYERS 10  /* Linear layers of the sample net (mlp.py:127-154) */
@@ -53,7 +53,7 @@ typedef struct hr_encode_group {
   float dir_mult, mom_mult;  /* pluecker multipliers (param.py:236-237)                     */
 } hr_encode_group;
 
-enum { HR_ISECT_Z_PLANE = 0, HR_ISECT_SPHERE = 1, HR_ISECT_CYLINDER = 2 };  /* z.py:16-97, primitive.py:366-438, :181-250 */
+enum { HR_ISECT_Z_PLANE = 0, HR_ISECT_SPHERE = 1, HR_ISECT_CYLINDER = 2, HR_ISECT_SPHERE_NEW = 3 };  /* z.py:16-97, primitive.py:366-438, :181-250, :440-546 */
 enum { HR_CONTRACT_NONE = 0, HR_CONTRACT_MIPNERF = 1, HR_CONTRACT_AFFINE = 2 };  /* AFFINE: bbox / z_depth (contract.py:65-110) */
 enum { HR_SHADE_SH = 0, HR_SHADE_RGB = 1 };
 enum { HR_DENSE_RELU = 0, HR_DENSE_SOFTPLUS = 1, HR_DENSE_RELU_ABS = 2 };
@@ -131,7 +131,7 @@ typedef struct hr_config {
   int32_t use_color_scale_shift; /* 'color_scale' reaches the colour net (tensorf_dynamic.py:780-784) */
   int32_t clamp_output; /* eval(): clamp(0,1) (tensorf_dynamic.py:805-806)              */
 
-  /* --- ABI 5 additions --- */
+  /* --- ABI 5 / 6 additions --- */
   /* HR_CONTRACT_AFFINE: c(p) = (p - min) / den per axis (BBoxContract :83-84: den = max - min; ZDepthContract :109-110:
    * min = 0, den = fac), distances are divided / multiplied by dist_fac (:77-81, :103-107).                             */
   float contract_affine_min[3], contract_affine_den[3];
@@ -140,6 +140,10 @@ typedef struct hr_config {
    * (scale_shift_color_one, utils/tensorf_utils.py:275-281; tensorf_dynamic.py:798-800); -1 = absent                 */
   int32_t off_cscale_global, off_cshift_global;
   hr_act act_cscale_global, act_cshift_global;
+  /* HR_ISECT_SPHERE_NEW (8 z channels: origin 3, resize 3, offset 1, radius 1; primitive.py:489-546):
+   * origin = z[0:3] * sphere_origin_scale, resize = z[3:6] * sphere_resize_scale + sphere_resize_initial           */
+  float sphere_resize_scale;
+  float sphere_resize_initial[3];
 } hr_config;
 
 /* Parameters in the reference's own state_dict layout, fp32, contiguous.

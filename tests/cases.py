@@ -34,6 +34,10 @@ CASES: Dict[str, dict] = {
     "donerf_cylinder": dict(builtin="donerf_sphere", over=dict(n_voxels=32 ** 3, variant=["cylinder", "outward_facing"]), n=192, seed=11, gain=30.0),
     "technicolor_global_color": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, variant="global_color"), n=128, seed=12, gain=30.0),
     "technicolor_both_color": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, variant="both_color"), n=128, seed=13, gain=30.0),
+    "shiny_scale_mask": dict(builtin="shiny_z_plane_tiny", over=dict(n_voxels=32 ** 3, variant="scale_mask"), n=192, seed=15, gain=30.0),
+    "technicolor_z_scale": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, variant="z_scale"), n=128, seed=16, gain=30.0),
+    "immersive_sphere_new": dict(builtin="neural_3d_z_plane", over=dict(n_voxels=32 ** 3, z_channels=32, variant=["sphere_new", "outward_facing"]), n=160, seed=17, gain=30.0),
+    "donerf_sphere_new": dict(builtin="donerf_sphere", over=dict(n_voxels=32 ** 3, variant="sphere_new"), n=192, seed=18, gain=30.0),
     "immersive_sphere_like": dict(builtin="neural_3d_z_plane", over=dict(n_voxels=32 ** 3, z_channels=32, variant=["sphere", "outward_facing"]), n=160, seed=14, gain=30.0),
 }
 

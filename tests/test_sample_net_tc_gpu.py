@@ -10,7 +10,7 @@ from tests.cases import CASES, build_case
 from tests.test_parity_gpu import GOLDEN, RGB_TOL, make_render
 
 pytestmark = pytest.mark.gpu
-TC_CASES = [n for n in CASES if n != "shiny_tiny"]  # the tensor-core path needs hidden width 256
+TC_CASES = [n for n, c in CASES.items() if c["builtin"] != "shiny_z_plane_tiny"]  # the tensor-core path needs hidden width 256
 
 
 @pytest.mark.parametrize("name", TC_CASES)
