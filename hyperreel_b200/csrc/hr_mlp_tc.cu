@@ -446,9 +446,10 @@ __global__ void pack_tc_pass(const float* __restrict__ W, const float* __restric
 }
 
 
-// Tensor map of the heads scratch [n rays][mlp_out] fp32, box = 16 columns x 32 rows (one epilogue warp's slice).
+// Tensor map of the heads scratch [n rays][mlp_out] fp32, box = box_cols columns x 32 rows (one epilogue warp's slice),
+// optionally with the 128-byte shared-memory swizzle (box_cols = 32).
 // The encoder comes from the driver through the runtime (no link-time libcuda dependency).  False = not available.
-bool make_heads_map(CUtensorMap* hmap, const float* heads, int mlp_out, long long n) {
+bool make_heads_map(CUtensorMap* hmap, const float* heads, int mlp_out, long long n, int box_cols, bool swizzle128) {
   memset(hmap, 0, sizeof(*hmap));
   if ((mlp_out % 4) != 0 || ((uintptr_t)heads % 16) != 0) return false;
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -465,11 +466,11 @@ bool make_heads_map(CUtensorMap* hmap, const float* heads, int mlp_out, long lon
   if (!encode) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)mlp_out, (cuuint64_t)n};
   cuuint64_t gstride[1] = {(cuuint64_t)mlp_out * sizeof(float)};
-  cuuint32_t box[2] = {16, 32};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(hmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)heads, gdim, gstride, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -580,7 +581,7 @@ static cudaError_t launch_mlp_tc_cs(const hr_config& cfg, const MlpTcPack& pk, c
   // tensor map of the heads scratch [n rays][mlp_out] fp32 for the last layer's TMA stores (box 16 cols x 32 rows)
   CUtensorMap hmap;
   static const int want_tma = getenv("HR_TC_TMA_STORE") ? atoi(getenv("HR_TC_TMA_STORE")) : 1;
-  const int use_tma = (want_tma && make_heads_map(&hmap, heads, cfg.mlp_out, n)) ? 1 : 0;
+  const int use_tma = (want_tma && make_heads_map(&hmap, heads, cfg.mlp_out, n, 16, false)) ? 1 : 0;
   cudaError_t le = cudaLaunchKernelEx(&lc, mlp_tc_kernel<CS>, cfg, pk, rays, heads, n, dbg_products, dbg_load_lo, trace, hmap, use_tma);
   if (want_trace) {
     unsigned long long h[256];

@@ -572,7 +572,7 @@ cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, const floa
   }
   CUtensorMap hmap;
   static const int want_tma = getenv("HR_TC_TMA_STORE") ? atoi(getenv("HR_TC_TMA_STORE")) : 1;
-  const int use_tma = (want_tma && make_heads_map(&hmap, heads, cfg.mlp_out, n)) ? 1 : 0;
+  const int use_tma = (want_tma && make_heads_map(&hmap, heads, cfg.mlp_out, n, 16, false)) ? 1 : 0;
   mlp_tc2_kernel<<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, stream>>>(cfg, pk, rays, heads, n, trace, hmap, use_tma, rays_copy);
   cudaError_t le = cudaGetLastError();
   if (want_trace) {

@@ -152,7 +152,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 }  // namespace tc
 
 // host helpers defined in hr_mlp_tc.cu
-bool make_heads_map(CUtensorMap* hmap, const float* heads, int mlp_out, long long n);
+bool make_heads_map(CUtensorMap* hmap, const float* heads, int mlp_out, long long n, int box_cols, bool swizzle128);
 void launch_pack_tc_pass(const float* W, const float* b, uint8_t* dst, float* bias_dst, int n, int first_chunk, int n_chunks,
                          int in_src, int mlp_in, int is_skip, int out_rows, int perm_S, int perm_stride, int out_col0,
                          cudaStream_t st);
