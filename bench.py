@@ -53,6 +53,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s: burst figure of MEASURED_PEAKS.json (cuBLAS 8192^3), else the nominal 2250."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", 0.0)), "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS burst)"
+    return 2250.0, 0.0, "nominal dense bf16 (B200_PROFILING.md fallback)"
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -241,6 +252,11 @@ def run_ours(args):
             mr, _, cores = time_cpu_port(cfg, ds, sd, sig, hb, 3, 1, CPU_SAMPLE_RAYS)
             cpu = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": "port",
                    "sample": f"{CPU_SAMPLE_RAYS} rays x {sig.n_samples} samples (bounded sample), torch CPU ops, 1 warm-up + 3 runs, median"}
+        # sample net (tensor-core bound): algorithmic MACs of the six Linear layers x 3 split products x 2 flop
+        macs = sum(o * i for o, i in sig.mlp_layer_shapes)
+        tpeak, tsust, tsrc = measured_tensor_peak()
+        products = 3 if args.mlp == "bf16x3" else 1
+        tach = (2.0 * products * macs * n / (tm["mlp_ms"] * 1e-3) / 1e12) if tm["mlp_ms"] > 0 else 0.0
         line = {
             "metric": "Mrays/s at 65k-ray x 32-sample batch", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -258,6 +274,11 @@ def run_ours(args):
                          "traffic": traffic, "kernel": "render_kernel (fused intersect+gather+decode+composite)",
                          "algorithmic_bytes_per_ray": bpr, "kernel_ms": tm["render_ms"], "peak_source": peak_src,
                          "sample_net_kernel_ms": tm["mlp_ms"]},
+            "roofline_sample_net": {"bound": "tensor" if args.mlp == "bf16x3" else "fp32 simt", "achieved": tach, "peak": tpeak,
+                                    "unit": "TFLOP/s", "frac": tach / tpeak if tpeak else None, "peak_sustained": tsust,
+                                    "kernel": "mlp_tc2_kernel (bf16 hi/lo split, 3 tcgen05.mma per k-step)" if args.mlp == "bf16x3" else "mlp_simt_kernel",
+                                    "algorithmic_macs_per_ray": macs, "executed_flop_per_ray": 2 * products * macs,
+                                    "kernel_ms": tm["mlp_ms"], "peak_source": tsrc},
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

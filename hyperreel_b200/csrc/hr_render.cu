@@ -194,7 +194,7 @@ __device__ __forceinline__ void group_products(const GroupTaps<C, DYN>& g, float
 }
 
 template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool STAGES>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (C1 + C2 == 0) ? 3 : 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (C1 + C2 == 0 || SPL == 1) ? 3 : 2)
 render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Derived dv,
               const __grid_constant__ RenderTabs tabs, const float* __restrict__ rays,
               const float* __restrict__ heads, float* __restrict__ rgb_out, long long n_rays, StageOut so,
