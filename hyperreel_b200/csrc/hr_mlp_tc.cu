@@ -6,17 +6,18 @@
 // i.e. three tcgen05.mma (kind::f16, bf16 inputs) per k-step; the dropped A_lo*B_lo term and the split
 // residuals are O(2^-16) relative per product (DESIGN.md "precision of the tensor-core sample net").
 //
-// One persistent CTA per SM, one 128-ray tile at a time (UMMA M = 128, one TMEM lane per ray):
-//   warps 0-15 epilogue (four per TMEM lane quadrant, alternating over 32-column chunks): thread = ray.  Encode the ray, then per layer read the accumulator from TMEM
-//              (tcgen05.ld 32x32b), add bias, LeakyReLU, split to bf16 hi/lo and write the next layer's A
-//              operand straight into shared memory in the UMMA K-major no-swizzle ("interleave") layout;
-//              The last layer is computed transposed (weights as the A operand): lane = output column, so each
-//              warp stores one coalesced 128-byte line per ray and the bias is a single register.
-//   warp 16    producer: streams the pre-packed weight images (one 16-wide k-step of one pass: bf16 hi and lo,
-//              already in UMMA layout) through a 4-stage ring with cp.async.bulk + mbarrier complete_tx.
-//   warp 17    MMA issuer: one lane issues tcgen05.mma / tcgen05.commit, trailing the epilogue chunk by chunk
-//              (a_ready barriers per 32-column chunk), with two 256-column TMEM accumulators ping-ponged
-//              across layers so layer l+1's MMAs overlap layer l's epilogue.
+// FIRST LAYOUT, kept selectable with HR_TC_V=1 for A/B measurements; the product path is hr_mlp_tc2.cu.
+// One persistent CTA per SM, one 128-ray tile at a time (UMMA M = 128, one TMEM lane per ray), 320 threads:
+//   warps 0-7  epilogue (two groups of four warps, thread = ray): encode the ray, then per layer read the accumulator from
+//              TMEM (tcgen05.ld 32x32b), add bias, LeakyReLU, split to bf16 hi/lo and write the next layer's A operand
+//              (hi AND lo, in place) into shared memory in the UMMA K-major no-swizzle layout; last layer: 16-column slices
+//              staged per warp and written with TMA tensor stores.
+//   warp 8     producer: streams the pre-packed weight images (one 16-wide k-step of one full-width pass, N <= 256)
+//              through a 3-stage ring with cp.async.bulk + mbarrier complete_tx.
+//   warp 9     MMA issuer: one lane issues tcgen05.mma / tcgen05.commit, trailing the epilogue chunk by chunk (a_ready
+//              barriers per 32-column chunk), two 256-column TMEM accumulators ping-ponged across layers.
+// Measured: 81 K cycles per tile (the in-place activation operand serialises layer l+1's MMAs behind layer l's epilogue
+// and the one-lane issue loop costs ~150 cycles per k-step of overhead); see profiles/r1_notes.md.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 
