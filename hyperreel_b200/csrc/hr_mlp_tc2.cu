@@ -88,7 +88,7 @@ __device__ __forceinline__ uint32_t ks_slot(int row, int kg) { return (uint32_t)
 __global__ void __launch_bounds__(tc2::NTHREADS, 1)
 mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ MlpTcPack pk, const float* __restrict__ rays,
                float* __restrict__ heads, long long n_rays, unsigned long long* trace,
-               const __grid_constant__ CUtensorMap heads_map, int use_tma_store, float* __restrict__ rays_copy) {
+               const __grid_constant__ CUtensorMap heads_map, int use_tma_store, float* __restrict__ rays_copy, int trace_iter) {
   using namespace tc2;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -143,7 +143,7 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
   // diagnostic timeline (HR_TC_TRACE): CTA 0, second tile; slot = pass * 8 + event
   const bool tracing = (trace != nullptr) && (blockIdx.x == 0);
   auto TR = [&](long long iter, int pass, int ev) {
-    if (tracing && iter == 1 && (threadIdx.x & 31) == 0) trace[pass * 8 + ev] = clock64();
+    if (tracing && iter == trace_iter && (threadIdx.x & 31) == 0) trace[pass * 8 + ev] = clock64();
   };
 
   if (warp == EPI_WARPS) {
@@ -573,7 +573,8 @@ cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, const floa
   CUtensorMap hmap;
   static const int want_tma = getenv("HR_TC_TMA_STORE") ? atoi(getenv("HR_TC_TMA_STORE")) : 1;
   const int use_tma = (want_tma && make_heads_map(&hmap, heads, cfg.mlp_out, n, 16, false)) ? 1 : 0;
-  mlp_tc2_kernel<<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, stream>>>(cfg, pk, rays, heads, n, trace, hmap, use_tma, rays_copy);
+  mlp_tc2_kernel<<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, stream>>>(cfg, pk, rays, heads, n, trace, hmap, use_tma, rays_copy,
+                                                                    getenv("HR_TC_TRACE_ITER") ? atoi(getenv("HR_TC_TRACE_ITER")) : 1);
   cudaError_t le = cudaGetLastError();
   if (want_trace) {
     unsigned long long hbuf[1024];
