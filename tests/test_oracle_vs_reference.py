@@ -58,3 +58,22 @@ def test_oracle_matches_live_reference_on_fresh_rays(name):
     n, S = case.rays.shape[0], case.n_samples
     assert (st["points"].reshape(n, -1) - out["_embed"]["points"]).abs().max() <= 2e-6
     assert (st["distances"] - out["_embed"]["distances"]).abs().max() <= 2e-6
+
+
+@pytest.mark.parametrize("name", ["technicolor_trained", "neural3d_trained", "donerf_trained", "immersive_sphere_new",
+                                  "donerf_cylinder", "technicolor_bbox"])
+def test_oracle_matches_reference_on_crafted_edge_rays(name):
+    """The rays of tests/test_edge_rays_gpu.py (plane-parallel, keyframe boundaries, far / centred origins, un-normalised
+    directions): the oracle must still equal the unmodified reference there before it may judge the CUDA path."""
+    from nlf.rendering import render_chunked
+    from tests.test_edge_rays_gpu import craft
+
+    case = build_case(name)
+    rays = craft(case)
+    ref = ref_shim.build_reference(case.model_cfg_plain, case.dataset)
+    ref.load_state_dict(case.state_dict, strict=False)
+    with torch.no_grad():
+        a = render_chunked(rays.clone(), ref, {}, rays.shape[0])["rgb"]
+    b = HyperReelOracle(case.model_cfg_plain, case.dataset, case.state_dict).render(rays.clone())
+    assert torch.isfinite(a).all()
+    assert float((a.reshape(b.shape) - b).abs().max()) <= 2e-6
