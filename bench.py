@@ -29,7 +29,7 @@ WORKLOAD = "technicolor_z_plane"
 N_VOXELS = 512000000  # final grid 1007x1007x503 (utils/tensorf_utils.py:65-68)
 DENSITY_GAIN = 30.0
 PARAM_SEED = 11
-CPU_SAMPLE_RAYS = 8192
+CPU_SAMPLE_RAYS = int(os.environ.get("HR_BENCH_CPU_RAYS", "8192"))  # bounded CPU sample (the env override is for the CPU test)
 L2_FLUSH_BYTES = 512 << 20
 
 
