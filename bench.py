@@ -183,23 +183,34 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    launches0 = model.launch_count()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    evs = []
-    for _ in range(args.steps):
-        flush.zero_()  # evict L2 between timed iterations (tables 62 MiB < 126 MB L2)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        step()
-        b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    launches = model.launch_count() - launches0
+    BAD = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
+    remeasured = False
+    while True:
+        launches0 = model.launch_count()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()  # evict L2 between timed iterations (tables 62 MiB < 126 MB L2)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        launches = model.launch_count() - launches0
+        # a timed region that saw a hardware / thermal slowdown is measured again, once (sw_power_cap is kept and reported)
+        bad = torch.tensor([1 if (not remeasured and any(r in BAD for r in sampler.summary()["reasons"])) else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()) == 0:
+            break
+        remeasured = True
+        time.sleep(2.0)
     # per-kernel durations for the roofline: a second pass with the library's CUDA events around each kernel (kept out of
     # the headline loop so the event records do not sit between the two kernels of a step)
     model.timing(True)
@@ -235,6 +246,12 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_val = world * n / (float(t2.item()) * 1e-3) / 1e6
+    # the timed regions last a few milliseconds, far less than one nvidia-smi poll: keep the same step running for about
+    # 1.5 s more (a fixed count, so that every rank issues the same number of collectives) so that the clock /
+    # throttle-reason samples are taken under this load
+    for _ in range(5000):
+        step()
+    torch.cuda.synchronize()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
@@ -269,7 +286,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n * sig.c_in * 4, "d2h_bytes_per_step": n * 12,
                     "ms_per_step": float(t2.item())},
             "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
+            "clocks": dict(sampler.summary(), remeasured=remeasured),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "kernel": "render_kernel (fused intersect+gather+decode+composite)",
                          "algorithmic_bytes_per_ray": bpr, "kernel_ms": tm["render_ms"], "peak_source": peak_src,
