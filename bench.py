@@ -284,7 +284,9 @@ def run_ours(args):
                        "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB memset)", "sample_net": args.mlp,
                        "params": f"seed {PARAM_SEED}, density gain {DENSITY_GAIN} (trained-like)"},
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n * sig.c_in * 4, "d2h_bytes_per_step": n * 12,
-                    "ms_per_step": float(t2.item())},
+                    "ms_per_step": float(t2.item()),
+                    "path": "hr_render_host: pinned rays read zero-copy over PCIe by the sample net's encoder warps (the H2D "
+                            "transfer, inside the timed region), rgb copied back D2H in two pieces; wall clock per call"},
             "gpu_launches": int(launches),
             "clocks": dict(sampler.summary(), remeasured=remeasured),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
