@@ -65,6 +65,7 @@ def test_oracle_matches_live_reference_on_fresh_rays(name):
 def test_oracle_matches_reference_on_crafted_edge_rays(name):
     """The rays of tests/test_edge_rays_gpu.py (plane-parallel, keyframe boundaries, far / centred origins, un-normalised
     directions): the oracle must still equal the unmodified reference there before it may judge the CUDA path."""
+    ref_shim.install()
     from nlf.rendering import render_chunked
     from tests.test_edge_rays_gpu import craft
 
@@ -77,3 +78,45 @@ def test_oracle_matches_reference_on_crafted_edge_rays(name):
     b = HyperReelOracle(case.model_cfg_plain, case.dataset, case.state_dict).render(rays.clone())
     assert torch.isfinite(a).all()
     assert float((a.reshape(b.shape) - b).abs().max()) <= 2e-6
+
+
+def test_oracle_matches_reference_on_every_shipped_yaml_that_lowers():
+    """Every model YAML the reference ships that the fused path accepts (34 of 51): build the unmodified reference from the
+    YAML itself (grid shrunk to 24^3 for speed), load seeded parameters, and hold the oracle to it on seeded rays.  This
+    pins the oracle's reading of the real configuration files, not only of the built-ins and their variants."""
+    import glob
+    import os
+
+    import hyperreel_b200 as hb
+    from hyperreel_b200.config import to_plain
+    from hyperreel_b200.signature import UnsupportedPipeline
+    from hyperreel_b200.state import seeded_state_dict
+
+    ref_shim.install()
+    from nlf.rendering import render_chunked
+
+    ds = {"num_keyframes": 12, "num_frames": 50, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y"}
+    checked, nonzero = 0, 0
+    for f in sorted(glob.glob(os.path.join(ref_shim.REFERENCE_ROOT, "conf/experiment/model/*.yaml"))):
+        cfg = hb.load_model_yaml(f)
+        if cfg is None:  # bom_z_plane.yaml is empty
+            continue
+        cfg.color.net.N_voxel_init = 24 ** 3
+        cfg.color.net.N_voxel_final = 24 ** 3
+        try:
+            sig = hb.lower(cfg, ds)
+        except UnsupportedPipeline:
+            continue
+        sd = seeded_state_dict(sig, seed=3, density_gain=30.0)
+        rays = hb.rays.for_signature(sig, 48, seed=9)
+        plain = to_plain(cfg)
+        ref = ref_shim.build_reference(plain, ds)
+        _, unexpected = ref.load_state_dict(sd, strict=False)
+        assert not unexpected, (f, unexpected)
+        with torch.no_grad():
+            a = render_chunked(rays.clone(), ref, {}, rays.shape[0])["rgb"]
+        b = HyperReelOracle(plain, ds, sd).render(rays.clone())
+        assert float((a.reshape(b.shape) - b).abs().max()) <= 2e-6, os.path.basename(f)
+        checked += 1
+        nonzero += int(float(b.abs().max()) > 0)
+    assert checked >= 34 and nonzero >= 30
