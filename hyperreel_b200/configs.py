@@ -221,6 +221,8 @@ def _apply_variant(cfg: Cfg, variant: str) -> None:
         for g in pred.params.values():
             if "pe" in g and g.pe is not None:
                 g.pe = to_cfg({"type": "basic", "n_freqs": int(g.pe.n_freqs), "freq_multiplier": 2.0})
+    elif variant == "wide_pe":  # stanford_z_plane_mem.yaml / immersive_cylinder_pe.yaml: more PE bands -> 33..64 input features
+        pred.params.ray.pe.n_freqs = 4
     elif variant == "bbox":  # technicolor_z_plane_world.yaml:143-147
         it.contract = to_cfg({"type": "bbox", "contract_samples": True, "bbox_min": [-2.0, -2.0, 0.5],
                               "bbox_max": [2.0, 2.0, -2.5]})

@@ -17,7 +17,7 @@
 
 namespace hr {
 cudaError_t launch_render(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
-                          const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
+                          const float* heads, float* rgb, long long n, const ExtraOut* so, int num_sms,
                           cudaStream_t stream, unsigned char* rgb8);
 cudaError_t launch_generate_rays(const hr_camera& cam, int c_in, long long first, long long n, float* out, cudaStream_t st);
 }  // namespace hr
@@ -43,6 +43,19 @@ static int fail(const char* fmt, ...) {
   g_err = buf;
   return 1;
 }
+
+// Every entry point runs with the handle's device current and restores the caller's device on the way out (the reference
+// never changes torch's current device; a stray cudaSetDevice here would silently move the caller's later allocations).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
 
 #define CK(expr)                                                                                   \
   do {                                                                                             \
@@ -139,10 +152,24 @@ int grid_for(long long total) {
   return (int)g;
 }
 
+// Packed-parameter storage.  hr_upload asks for its buffers in a fixed order; a buffer whose size is unchanged since the
+// previous upload is reused, so a parameter refresh (same grid, same net) performs no cudaFree / cudaMalloc.
 int dev_alloc(hr_handle* h, void** p, size_t bytes) {
-  cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+  bytes = bytes ? bytes : 16;
+  const size_t i = h->slot_cursor++;
+  if (i < h->slots.size() && h->slots[i].bytes == bytes) {
+    *p = h->slots[i].ptr;
+    return 0;
+  }
+  if (i < h->slots.size()) {
+    cudaFree(h->slots[i].ptr);
+    h->slots[i] = {nullptr, 0};
+  } else {
+    h->slots.push_back({nullptr, 0});
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess) return fail("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-  h->owned.push_back(*p);
+  h->slots[i] = {*p, bytes};
   return 0;
 }
 
@@ -164,7 +191,7 @@ int stage_in(const float* src, size_t count, int on_device, cudaStream_t st, std
 
 int validate(const hr_config& c) {
   if (c.abi_version != HR_ABI_VERSION) return fail("hr_config.abi_version %d != %d", c.abi_version, HR_ABI_VERSION);
-  if (c.c_in < 6 || c.c_in > 16) return fail("unsupported c_in %d", c.c_in);
+  if (c.c_in != 6 && c.c_in != 8) return fail("unsupported c_in %d (6: static rays, 8: video rays)", c.c_in);
   if (c.n_groups < 1 || c.n_groups > HR_MAX_GROUPS) return fail("unsupported n_groups %d", c.n_groups);
   if (c.mlp_layers < 2 || c.mlp_layers > HR_MAX_LAYERS) return fail("unsupported mlp_layers %d", c.mlp_layers);
   if (c.mlp_width != 128 && c.mlp_width != 256) return fail("unsupported mlp_width %d (128 or 256)", c.mlp_width);
@@ -199,7 +226,6 @@ int validate(const hr_config& c) {
   if (c.shading == HR_SHADE_RGB && c.app_dim != 3) return fail("RGB shading needs app_dim 3");
   if (c.shading != HR_SHADE_SH && c.shading != HR_SHADE_RGB) return fail("unsupported shading");
   if (c.mlp_mode != HR_MLP_FP32_SIMT && c.mlp_mode != HR_MLP_BF16X3_TC) return fail("unsupported mlp_mode");
-  if (c.mlp_mode == HR_MLP_BF16X3_TC && c.mlp_width != 256) return fail("tensor-core sample net needs width 256");
   return 0;
 }
 
@@ -238,7 +264,7 @@ int hr_create(const hr_config* cfg, int device, hr_handle** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail("hr_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-  CK(cudaSetDevice(device));
+  DeviceGuard guard(device);
   hr_handle* h = new (std::nothrow) hr_handle();
   if (!h) return fail("hr_create: out of memory");
   h->cfg = *cfg;
@@ -256,13 +282,13 @@ static void drop_host_graph(hr_handle* h);
 
 int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
   if (!h || !p) return fail("hr_upload: null argument");
-  CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   drop_host_graph(h);
   cudaStream_t st = (cudaStream_t)stream;
   const hr_config& c = h->cfg;
-  // release any previous pack
-  for (void* q : h->owned) cudaFree(q);
-  h->owned.clear();
+  // Buffers of the previous pack are reused slot by slot when their sizes are unchanged (dev_alloc).  Work already
+  // enqueued on `st` that reads the old contents is ordered before the pack kernels below (same stream).
+  h->slot_cursor = 0;
   h->uploaded = false;
   h->tc_ready = false;
   std::vector<void*> temps;
@@ -299,9 +325,7 @@ int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
     h->simt.Np[l] = Np;
   }
   if (!rc && c.mlp_mode == HR_MLP_BF16X3_TC) {
-    // HR_TC_V=1 keeps the first tensor-core layout (hr_mlp_tc.cu) selectable for A/B measurements
-    static const int tc_version = getenv("HR_TC_V") ? atoi(getenv("HR_TC_V")) : 2;
-    rc = (tc_version == 1) ? hr::pack_mlp_tc(h, p, w_dev, b_dev, st) : hr::pack_mlp_tc2(h, p, w_dev, b_dev, st);
+    rc = hr::pack_mlp_tc2(h, w_dev, b_dev, st);
     if (!rc) h->tc_ready = true;
   }
 
@@ -385,9 +409,14 @@ int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
   }
   cudaError_t le = cudaGetLastError();
   if (!rc && le != cudaSuccess) rc = fail("hr_upload: pack kernel launch failed: %s", cudaGetErrorString(le));
-  if (!temps.empty()) {
+  if (!temps.empty()) {  // host sources only: the staging copies must outlive the pack kernels
     cudaStreamSynchronize(st);
     for (void* t : temps) cudaFree(t);
+  }
+  // slots past the cursor belong to a previous, larger layout
+  while (h->slots.size() > h->slot_cursor) {
+    cudaFree(h->slots.back().ptr);
+    h->slots.pop_back();
   }
   if (rc) return rc;
   h->uploaded = true;
@@ -413,8 +442,7 @@ static int launch_sample_net(hr_handle* h, const float* rays, int64_t n, float* 
   cudaError_t e;
   if (c.mlp_mode == HR_MLP_BF16X3_TC) {
     if (!h->tc_ready) return fail("hr_render: tensor-core pack missing");
-    e = (h->tc.version == 2) ? hr::launch_mlp_tc2(c, h->tc, rays, heads, n, h->num_sms, st)
-                             : hr::launch_mlp_tc(c, h->tc, rays, heads, n, h->num_sms, st);
+    e = hr::launch_mlp_tc2(c, h->tc, h->tma_encode, rays, heads, n, h->num_sms, st);
   } else {
     e = hr::launch_mlp_simt(c, h->simt, rays, heads, n, h->num_sms, st);
   }
@@ -423,7 +451,7 @@ static int launch_sample_net(hr_handle* h, const float* rays, int64_t n, float* 
   return 0;
 }
 
-static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, float* mlp_out, const hr::StageOut* so,
+static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, float* mlp_out, const hr::ExtraOut* so,
                        void* workspace, int64_t ws_bytes, cudaStream_t st, unsigned char* rgb8 = nullptr) {
   if (!h) return fail("hr_render: null handle");
   if (!h->uploaded) return fail("hr_render: parameters not uploaded (call hr_upload)");
@@ -462,20 +490,48 @@ static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, f
 
 int hr_render(hr_handle* h, const float* rays, int64_t n_rays, float* rgb, void* workspace, int64_t workspace_bytes,
               void* stream) {
-  if (h) CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h ? h->device : 0);
   return render_impl(h, rays, n_rays, rgb, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int hr_render_stages(hr_handle* h, const float* rays, int64_t n_rays, float* rgb, float* mlp_out, float* distances,
-                     float* points, float* sigma, float* weights, void* workspace, int64_t workspace_bytes, void* stream) {
-  if (h) CK(cudaSetDevice(h->device));
-  hr::StageOut so{distances, points, sigma, weights};
+                     float* points, float* sigma, float* weights, float* rgb_samples, void* workspace, int64_t workspace_bytes,
+                     void* stream) {
+  DeviceGuard guard(h ? h->device : 0);
+  hr::ExtraOut so{};
+  so.distances = distances; so.points = points; so.sigma = sigma; so.weights = weights; so.rgb_samples = rgb_samples;
   return render_impl(h, rays, n_rays, rgb, mlp_out, &so, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int hr_render_fields(hr_handle* h, const float* rays, int64_t n_rays, float* rgb, float* render_weights,
+                     const hr_field_request* req, int32_t n_req, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h) return fail("hr_render_fields: null handle");
+  if (n_req < 0 || (n_req > 0 && !req)) return fail("hr_render_fields: bad request list");
+  DeviceGuard guard(h->device);
+  const hr_config& c = h->cfg;
+  hr::ExtraOut so{};
+  so.weights = render_weights;
+  for (int i = 0; i < n_req; ++i) {
+    const int f = req[i].field, m = req[i].mode;
+    if (f < 0 || f >= HR_N_FIELDS) return fail("hr_render_fields: unknown field %d", f);
+    if (m != HR_FIELD_OVER && m != HR_FIELD_NO_OVER && m != HR_FIELD_PRED_WEIGHTS) return fail("hr_render_fields: unknown mode %d", m);
+    if (!req[i].out) return fail("hr_render_fields: null output for field %d", f);
+    if (so.field_out[f]) return fail("hr_render_fields: field %d requested twice", f);
+    // fields the pipeline does not carry (reference: KeyError on x[key])
+    if ((f == HR_FIELD_BASE_TIMES || f == HR_FIELD_TIME_OFFSET) && !(c.dynamic || c.use_flow))
+      return fail("hr_render_fields: this pipeline has no keyframe times");
+    const int head_off[HR_N_FIELDS] = {0, 0, 0, 0, 0, 0, 0, c.off_cscale, c.off_cshift, c.off_flow, c.off_sigma,
+                                       c.off_point_sigma, c.off_offset};
+    if (f >= HR_FIELD_COLOR_SCALE && head_off[f] < 0) return fail("hr_render_fields: the sample net has no head for field %d", f);
+    so.field_out[f] = req[i].out;
+    so.field_mode[f] = m;
+  }
+  return render_impl(h, rays, n_rays, rgb, nullptr, &so, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int hr_render_to8b(hr_handle* h, const float* rays, int64_t n_rays, uint8_t* rgb8, void* workspace, int64_t workspace_bytes,
                    void* stream) {
-  if (h) CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h ? h->device : 0);
   if (!rgb8) return fail("hr_render_to8b: null output");
   return render_impl(h, rays, n_rays, nullptr, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream, rgb8);
 }
@@ -494,7 +550,7 @@ int hr_generate_rays(const hr_camera* cam, int32_t c_in, int64_t first_pixel, in
 int hr_render_frame_to8b_host(hr_handle* h, const hr_camera* cam, uint8_t* rgb8_host, int64_t chunk) {
   if (!h || !cam || !rgb8_host) return fail("hr_render_frame_to8b_host: null argument");
   if (!h->uploaded) return fail("hr_render_frame_to8b_host: parameters not uploaded");
-  CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const hr_config& c = h->cfg;
   const int64_t n_rays = (int64_t)cam->width * cam->height;
   if (chunk <= 0) chunk = (h->cfg.mlp_mode == HR_MLP_BF16X3_TC) ? (int64_t)h->num_sms * 128 * 14 : 262144;  // whole tile waves
@@ -512,7 +568,7 @@ int hr_render_frame_to8b_host(hr_handle* h, const hr_camera* cam, uint8_t* rgb8_
     }
     P.ws_bytes = hr_workspace_bytes(h, chunk);
     for (int i = 0; i < 3; ++i) {
-      CK(cudaMalloc((void**)&P.d_rays[i], (size_t)chunk * 8 * sizeof(float)));
+      CK(cudaMalloc((void**)&P.d_rays[i], (size_t)chunk * c.c_in * sizeof(float)));
       CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)chunk * 3 * sizeof(float)));
       CK(cudaMalloc(&P.d_ws[i], (size_t)P.ws_bytes));
     }
@@ -538,17 +594,15 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
   if (!h->uploaded) return fail("hr_render_host: parameters not uploaded");
   if (n_rays == 0) return 0;
   if (!rays_host || !rgb_host) return fail("hr_render_host: null buffer");
-  CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const hr_config& c = h->cfg;
   HostPipe& P = h->pipe;
   const int64_t wave = (int64_t)h->num_sms * 128;  // one full wave of 128-ray tiles of the tensor-core sample net
   // Default (chunk <= 0), tensor-core net, batches of a few waves: the "wave split" pipeline below.  Otherwise chunks of
   // `chunk` rays (default: whole waves for the tensor-core net, 32 768 rays for the CUDA-core net) on three streams.
-  static const int allow_split = getenv("HR_HOST_SPLIT") ? atoi(getenv("HR_HOST_SPLIT")) : 1;
   const bool whole = chunk <= 0 && c.mlp_mode == HR_MLP_BF16X3_TC && n_rays <= 16 * wave;  // the batch stays whole on the device
   const float* rays_dev_view = nullptr;
-  static const int allow_zero_copy = getenv("HR_HOST_ZERO_COPY") ? atoi(getenv("HR_HOST_ZERO_COPY")) : 1;
-  if (allow_zero_copy && whole && h->tc_ready && h->tc.version == 2 && !h->timing) {
+  if (whole && h->tc_ready && !h->timing) {
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, rays_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr)
       rays_dev_view = (const float*)pa.devicePointer;
@@ -556,7 +610,7 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
       cudaGetLastError();  // pageable memory: not an error, just not device-addressable
   }
   const bool zero_copy = rays_dev_view != nullptr;
-  const bool split = !zero_copy && allow_split && whole && n_rays > wave;
+  const bool split = !zero_copy && whole && n_rays > wave;
   if (chunk <= 0) chunk = (c.mlp_mode == HR_MLP_BF16X3_TC) ? wave : 32768;
   if (chunk > n_rays) chunk = n_rays;
   const int64_t alloc = (split || zero_copy) ? n_rays : chunk;  // rays per device slot
@@ -571,7 +625,7 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
     }
     P.ws_bytes = hr_workspace_bytes(h, alloc);
     for (int i = 0; i < 3; ++i) {
-      CK(cudaMalloc((void**)&P.d_rays[i], (size_t)alloc * 8 * sizeof(float)));
+      CK(cudaMalloc((void**)&P.d_rays[i], (size_t)alloc * c.c_in * sizeof(float)));
       CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)alloc * 3 * sizeof(float)));
       CK(cudaMalloc(&P.d_ws[i], (size_t)P.ws_bytes));
     }
@@ -643,7 +697,7 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
     float* d_rays = P.d_rays[0];
     float* d_rgb = P.d_rgb[0];
     float* heads = (float*)P.d_ws[0];
-    cudaError_t e = hr::launch_mlp_tc2(c, h->tc, rays_dev_view, heads, n_rays, h->num_sms, s0, d_rays);
+    cudaError_t e = hr::launch_mlp_tc2(c, h->tc, h->tma_encode, rays_dev_view, heads, n_rays, h->num_sms, s0, d_rays);
     if (e != cudaSuccess) return fail("sample-net launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
     const int pieces = 2;
@@ -662,10 +716,9 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
     return 0;
   };
   auto enqueue = [&]() -> int { return zero_copy ? enqueue_zero_copy() : (split ? enqueue_split() : enqueue_chunks()); };
-  static const int use_graph = getenv("HR_HOST_GRAPH") ? atoi(getenv("HR_HOST_GRAPH")) : 1;
   const int64_t n_chunks = (n_rays + chunk - 1) / chunk;
   const int64_t key_chunk = zero_copy ? -2 : (split ? -1 : chunk);
-  if (use_graph && !h->timing && (zero_copy || split || n_chunks > 1)) {
+  if (!h->timing && (zero_copy || split || n_chunks > 1)) {
     // Launch-bound when issued call by call: capture the whole multi-stream pipeline once per (buffers, size) signature
     // and replay it with a single graph launch.
     if (!(P.graph && P.g_rays == rays_host && P.g_rgb == rgb_host && P.g_n == n_rays && P.g_chunk == key_chunk)) {
@@ -741,8 +794,9 @@ int hr_timing_read(hr_handle* h, double* render_ms_avg, double* mlp_ms_avg, int6
 
 int hr_destroy(hr_handle* h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
-  for (void* q : h->owned) cudaFree(q);
+  DeviceGuard guard(h->device);
+  for (auto& sl : h->slots) cudaFree(sl.ptr);
+  hr::free_mlp_tc2(h);
   drop_events(h->ev_render);
   drop_events(h->ev_mlp);
   for (int i = 0; i < 3; ++i) {

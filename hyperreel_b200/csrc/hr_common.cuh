@@ -41,12 +41,19 @@ struct Derived {
   int kt;               // rows of the (axis, time) planes = number of keyframes
 };
 
-// Optional per-sample dumps for stage-boundary parity tests (all may be null).
-struct StageOut {
-  float* distances;  // [n,S]
-  float* points;     // [n,S,3]
-  float* sigma;      // [n,S]
-  float* weights;    // [n,S]
+// Outputs beyond rgb, produced by the EXTRA variant of the render kernel (all pointers may be null):
+//   * per-sample dumps for stage-boundary parity tests (hr_render_stages);
+//   * the extra composited fields of the reference's colour nets (tensorf_dynamic.py:808-837, tensorf_no_sample.py:254-278):
+//     field_out[f] receives sum_s w_s * x[f]_s ([n, dim], HR_FIELD_OVER), sum_s pred_w_s * x[f]_s (HR_FIELD_PRED_WEIGHTS) or
+//     the per-sample values themselves ([n, S*dim], HR_FIELD_NO_OVER).
+struct ExtraOut {
+  float* distances;    // [n,S]
+  float* points;       // [n,S,3]
+  float* sigma;        // [n,S]
+  float* weights;      // [n,S]
+  float* rgb_samples;  // [n,S,3] shaded colour of every sample before the colour transform, 0 where w <= rm_weight_mask_thre
+  float* field_out[HR_N_FIELDS];
+  int field_mode[HR_N_FIELDS];
 };
 
 __device__ __forceinline__ float apply_act(const hr_act& a, float x) {

@@ -34,11 +34,16 @@ struct hr_handle {
   int device = 0;
   int num_sms = 148;
   bool uploaded = false;
-  std::vector<void*> owned;  // device allocations of packed parameters
+  struct Slot { void* ptr; size_t bytes; };
+  std::vector<Slot> slots;   // device allocations of packed parameters, in hr_upload's request order
+  size_t slot_cursor = 0;
   hr::RenderTabs tabs;
   hr::MlpSimtPack simt;
   hr::MlpTcPack tc;
   bool tc_ready = false;
+  size_t tc_alloc_bytes = 0;  // current allocation behind tc.wpack / tc.bias (reused while the layout is unchanged)
+  int tc_alloc_bias = 0;
+  void* tma_encode = nullptr; // cuTensorMapEncodeTiled, from cudaGetDriverEntryPoint
   int64_t launches = 0;
   bool timing = false;
   std::vector<EventPair> ev_render, ev_mlp;

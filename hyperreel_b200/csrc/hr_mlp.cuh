@@ -20,13 +20,13 @@ struct MlpSimtPack {
   int skip;
 };
 
-// tcgen05 path (HR_MLP_BF16X3_TC): see hr_mlp_tc.cu.  A "pass" is one accumulator's worth of output columns
-// (a hidden layer, or <=256 columns of the last layer); its weights are stored as n_chunks*2 k-step images.
+// tcgen05 path (HR_MLP_BF16X3_TC): see hr_mlp_tc2.cu.  A "pass" is one accumulator's worth of output columns
+// (128 columns of a hidden layer or of the last layer); its weights are stored as n_chunks*2 k-step images.
 #define HR_TC_MAX_PASSES 24
 struct TcPass {
   int layer;        // Linear layer index
   int n;            // output columns of this pass (multiple of 16, <= 256)
-  int first_chunk;  // first A chunk consumed (0 = encoded input, 1.. = hidden)
+  int first_chunk;  // first A chunk consumed (0 = encoded input, in_chunks = first hidden chunk)
   int n_chunks;     // chunks of 32 k
   int bias_off;     // offset into the bias table
   int is_final;     // last layer: results go to HBM instead of the next A operand
@@ -39,7 +39,7 @@ struct MlpTcPack {
   long long wpack_bytes;
   int n_passes;
   int bias_count;
-  int version;         // 1 = hr_mlp_tc.cu (full-width passes, A in shared memory), 2 = hr_mlp_tc2.cu (half passes, A_hi in TMEM)
+  int in_chunks;       // 32-wide k-chunks of the encoded input (1: mlp_in <= 32, 2: mlp_in <= 64)
   TcPass passes[HR_TC_MAX_PASSES];
 };
 
@@ -47,16 +47,15 @@ size_t mlp_simt_smem_bytes(const MlpSimtPack& pk, int W);
 cudaError_t launch_mlp_simt(const hr_config& cfg, const MlpSimtPack& pk, const float* rays, float* heads,
                             long long n, int num_sms, cudaStream_t stream);
 
-cudaError_t launch_mlp_tc(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
-                          int num_sms, cudaStream_t stream);
-// rays may point to pinned host memory (read once, by the encoder warps); rays_copy (optional) receives a device copy
-cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n,
-                           int num_sms, cudaStream_t stream, float* rays_copy = nullptr);
+// rays may point to pinned host memory (read once, by the encoder warps); rays_copy (optional) receives a device copy;
+// tma_encode = the driver's cuTensorMapEncodeTiled (hr_handle::tma_encode)
+cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, void* tma_encode, const float* rays, float* heads,
+                           long long n, int num_sms, cudaStream_t stream, float* rays_copy = nullptr);
 }  // namespace hr
 
 struct hr_handle;
 struct hr_params;
 namespace hr {
-int pack_mlp_tc(hr_handle* h, const hr_params* p, const float* const* w_dev, const float* const* b_dev, cudaStream_t st);
-int pack_mlp_tc2(hr_handle* h, const hr_params* p, const float* const* w_dev, const float* const* b_dev, cudaStream_t st);
+int pack_mlp_tc2(hr_handle* h, const float* const* w_dev, const float* const* b_dev, cudaStream_t st);
+void free_mlp_tc2(hr_handle* h);
 }

@@ -1,9 +1,12 @@
-// Sample-prediction network on the 5th-generation tensor cores, second layout (MlpTcPack::version == 2).
+// Sample-prediction network on the 5th-generation tensor cores (HR_MLP_BF16X3_TC).
 //
-// Same math and the same bf16x3 split as hr_mlp_tc.cu (reference: nlf/nets/mlp.py:159-172 behind
-// nlf/embedding/ray.py:320-326):   D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo   with fp32 accumulation in TMEM.
+// Math (reference: nlf/nets/mlp.py:159-172 behind nlf/embedding/ray.py:320-326): every fp32 operand x is split into
+// bf16 hi = rn(x) and lo = rn(x - hi) and each Linear layer is
+//     D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo          (three tcgen05.mma kind::f16 per k-step, fp32 accumulation in TMEM);
+// the dropped A_lo*B_lo term and the split residuals are O(2^-16) relative per product.
+// Hidden width 128 or 256, encoded input up to 64 features (one or two 32-wide input chunks).
 //
-// What changed is where the activation operand lives, so that the tensor pipe never waits for an epilogue:
+// Where the activation operand lives, so that the tensor pipe never waits for an epilogue:
 //   * every Linear layer is issued as two half passes of N = 128 output columns (the last layer as ceil(out/128) parts),
 //     alternating between two 128-column TMEM accumulators D0 / D1;
 //   * the activation operand is double buffered across layers: layer l reads A(l) from buffer l&1 while the epilogue
@@ -12,7 +15,7 @@
 //   * A_hi (used by two of the three products) lives in TMEM (2 x 128 columns of packed bf16 pairs, written with
 //     tcgen05.st, consumed as the TMEM A operand), A_lo (used once) in shared memory (2 x 64 KB, UMMA K-major
 //     no-swizzle).  Per k-step the tensor pipe reads 4 KB (A_lo) + 3 x 4 KB (weights) of shared memory instead of
-//     3 x 4 KB + 3 x 8 KB, which was the measured limiter of the first layout (profiles/r1_notes.md).
+//     3 x 4 KB + 3 x 8 KB of an all-in-shared-memory layout (the measured limiter of the first version, profiles/r1_notes.md).
 //   TMEM map (512 columns): [0,128) A_hi buffer 0 | [128,256) A_hi buffer 1 | [256,384) D0 | [384,512) D1.
 //
 // Warp roles (384 threads, one persistent CTA per SM, one 128-ray tile at a time):
@@ -23,7 +26,8 @@
 //   warp 9      MMA issuer: the whole warp runs the loop, the tcgen05 instructions are guarded by elect.sync (ptxas then
 //               keeps all operands in uniform registers; inside `if (lane == 0)` it wraps every UTCHMMA in an ELECT/branch
 //               loop and the issue rate, not the tensor pipe, bounds an N = 128 layout).
-//   warps 10-11 ray encoders: RayParam + WindowedPE of the NEXT tile into the other encoded-input buffer.
+//   warps 10-11 ray encoders: RayParam + WindowedPE of the NEXT tile into the other encoded-input buffer (inputs wider than
+//               32 features have one buffer, released after the skip layer so the encode still hides under layers 4..).
 // Measured on B200 (profiles/r1_notes.md): 51 K cycles per tile in steady state (14 passes x 3.3-3.7 K) against 81 K for
 // the first layout; the kernel now runs power-limited (~1.68 GHz SM clock under this tensor load).
 #include <cuda.h>
@@ -56,7 +60,8 @@ constexpr int STG_BOXES = 4;         // 32 x 16 fp32 TMA-store boxes per epilogu
 // shared memory map (bytes)
 constexpr int ALO_BUF_BYTES = NKSTEP * KSTEP_BYTES;          // 64 KB per A_lo buffer
 constexpr int OFF_ALO = 0;                                   // [2 buffers][16 k-steps][4 KB]
-constexpr int X_BUF_BYTES = 4 * KSTEP_BYTES;                 // encoded input of one tile: 2 k-steps (32 k) x (hi, lo)
+constexpr int X_BUF_BYTES = 4 * KSTEP_BYTES;                 // encoded input of one tile: 2 k-steps (32 k) x (hi, lo); a 64-wide
+                                                             // input uses both buffers as one: 4 k-steps x (hi, lo)
 constexpr int OFF_X = OFF_ALO + 2 * ALO_BUF_BYTES;           // 131072: [2 tiles][hi 8 KB | lo 8 KB]
 constexpr int OFF_B = OFF_X + 2 * X_BUF_BYTES;               // 163840
 constexpr int OFF_BIAS = OFF_B + NSTAGE * STAGE_BYTES;       // 212992
@@ -88,7 +93,7 @@ __device__ __forceinline__ uint32_t ks_slot(int row, int kg) { return (uint32_t)
 __global__ void __launch_bounds__(tc2::NTHREADS, 1)
 mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ MlpTcPack pk, const float* __restrict__ rays,
                float* __restrict__ heads, long long n_rays, unsigned long long* trace,
-               const __grid_constant__ CUtensorMap heads_map, int use_tma_store, float* __restrict__ rays_copy, int trace_iter) {
+               const __grid_constant__ CUtensorMap heads_map, float* __restrict__ rays_copy, int trace_iter) {
   using namespace tc2;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -176,11 +181,17 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
     {
       uint32_t stage = 0, phase = 0, gp = 0, titer = 0;
       const uint32_t n_hidden = (uint32_t)cfg.mlp_layers - 1u;
+      const int in_chunks = pk.in_chunks;            // 32-wide chunks of the encoded input: 1 or 2
+      const bool x_double = (in_chunks == 1);        // two encoded-input buffers (tile parity) or one
       const uint64_t xdesc_hi0 = umma_desc(sbase + OFF_X, 2048, 128);
-      const uint64_t xdesc_lo0 = umma_desc(sbase + OFF_X + 2 * KSTEP_BYTES, 2048, 128);
+      const uint64_t xdesc_lo0 = umma_desc(sbase + OFF_X + 2 * in_chunks * KSTEP_BYTES, 2048, 128);
       const uint32_t full0 = bar(BAR_FULL), empty0 = bar(BAR_EMPTY), aready0 = bar(BAR_AREADY);
-      int p_x = 0;  // last pass of the first layer
-      while (p_x + 1 < n_passes && pk.passes[p_x + 1].layer == 0) ++p_x;
+      // Pass after which the encoders may write the next tile's input.  Two buffers: the last pass of the first layer
+      // (everything that read the *other* buffer -- the previous tile's first and skip layers -- was issued before it).
+      // One buffer: the last pass that reads the input at all (skip layer, else first layer).
+      int p_x = 0;
+      for (int p = 0; p < n_passes; ++p)
+        if (pk.passes[p].first_chunk == 0 && (pk.passes[p].layer == 0 || !x_double)) p_x = p;
       for (long long iter = 0; iter < n_iters; ++iter, ++titer) {
         for (int p = 0; p < n_passes; ++p, ++gp) {
           const int Pn = pk.passes[p].n, Player = pk.passes[p].layer, Pfirst = pk.passes[p].first_chunk;
@@ -199,38 +210,42 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
           uint32_t acc = 0;
           int n_h = Pchunks;
           if (Pfirst == 0) {
-            // ---- encoded input (32 k): both halves of the split come from shared memory ----
-            --n_h;
+            // ---- encoded input (32 k per chunk): both halves of the split come from shared memory ----
+            n_h -= in_chunks;
             // written once per tile (during the previous tile); only the first layer has to wait for it
             if (Player == 0 && Pwait) mbar_wait(aready0, titer & 1);
-            const uint64_t xoff = (uint64_t)(((titer & 1u) * X_BUF_BYTES) >> 4);
-            const uint64_t xdesc_hi = xdesc_hi0 + xoff, xdesc_lo = xdesc_lo0 + xoff;
-            mbar_wait(full0 + stage * 8, phase);
-            tc_fence_after();
-            const uint64_t woff = (uint64_t)((stage * STAGE_BYTES) >> 4);
-            asm volatile(
-                "{\n\t"
-                ".reg .pred e, q;\n\t"
-                ".reg .b64 xh1, xl1, wh1, wl1;\n\t"
-                "elect.sync _|e, 0xffffffff;\n\t"
-                "setp.eq.b32 q, %5, %5;\n\t"
-                "add.s64 xh1, %1, 256;\n\t"
-                "add.s64 xl1, %2, 256;\n\t"
-                "add.s64 wh1, %3, %7;\n\t"
-                "add.s64 wl1, %4, %7;\n\t"
-                "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, !q;\n\t"
-                "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, q;\n\t"
-                "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, q;\n\t"
-                "@e tcgen05.mma.cta_group::1.kind::f16 [%0], xh1, wh1, %5, q;\n\t"
-                "@e tcgen05.mma.cta_group::1.kind::f16 [%0], xl1, wh1, %5, q;\n\t"
-                "@e tcgen05.mma.cta_group::1.kind::f16 [%0], xh1, wl1, %5, q;\n\t"
-                "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
-                "}" ::"r"(d_tmem),
-                "l"(xdesc_hi), "l"(xdesc_lo), "l"(wdesc_hi0 + woff), "l"(wdesc_lo0 + woff), "r"(idesc), "r"(empty0 + stage * 8),
-                "l"(img)
-                : "memory");
-            acc = 1;
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            const uint64_t xoff = x_double ? (uint64_t)(((titer & 1u) * X_BUF_BYTES) >> 4) : 0ull;
+            for (int ic = 0; ic < in_chunks; ++ic) {
+              const uint64_t coff = xoff + (uint64_t)((ic * 2 * KSTEP_BYTES) >> 4);
+              const uint64_t xdesc_hi = xdesc_hi0 + coff, xdesc_lo = xdesc_lo0 + coff;
+              mbar_wait(full0 + stage * 8, phase);
+              tc_fence_after();
+              const uint64_t woff = (uint64_t)((stage * STAGE_BYTES) >> 4);
+              asm volatile(
+                  "{\n\t"
+                  ".reg .pred e, p, q;\n\t"
+                  ".reg .b64 xh1, xl1, wh1, wl1;\n\t"
+                  "elect.sync _|e, 0xffffffff;\n\t"
+                  "setp.ne.b32 p, %8, 0;\n\t"
+                  "setp.eq.b32 q, %5, %5;\n\t"
+                  "add.s64 xh1, %1, 256;\n\t"
+                  "add.s64 xl1, %2, 256;\n\t"
+                  "add.s64 wh1, %3, %7;\n\t"
+                  "add.s64 wl1, %4, %7;\n\t"
+                  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, p;\n\t"
+                  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, q;\n\t"
+                  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, q;\n\t"
+                  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], xh1, wh1, %5, q;\n\t"
+                  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], xl1, wh1, %5, q;\n\t"
+                  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], xh1, wl1, %5, q;\n\t"
+                  "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+                  "}" ::"r"(d_tmem),
+                  "l"(xdesc_hi), "l"(xdesc_lo), "l"(wdesc_hi0 + woff), "l"(wdesc_lo0 + woff), "r"(idesc), "r"(empty0 + stage * 8),
+                  "l"(img), "r"(acc)
+                  : "memory");
+              acc = 1;
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
           }
           // ---- hidden activations: A_hi from TMEM (8 packed columns per k-step), A_lo from shared memory ----
           const uint32_t a_par = (titer * n_hidden + (uint32_t)(Player - 1)) & 1u;
@@ -278,11 +293,10 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
               "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar(BAR_DFULL + db))
               : "memory");  // accumulator complete -> epilogue
           if (p == p_x) {
-            // Everything that read the other encoded-input buffer (the previous tile's first and skip layers) was issued
-            // before this point, and this tile's wait on the input barrier is behind us: the encoders may fill it.
+            // see p_x above: the encoders may now fill the next tile's input buffer
             asm volatile(
                 "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-                "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar(BAR_XFREE + ((titer + 1u) & 1u)))
+                "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar(BAR_XFREE + (x_double ? ((titer + 1u) & 1u) : 0u)))
                 : "memory");
           }
           TR(iter, p, 3);
@@ -296,9 +310,12 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
     // issuer (BAR_XFREE) once the previous tile's readers have retired.
     const int et = (warp - (EPI_WARPS + 2)) * 32 + lane;  // 0 .. 63
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(rays) | reinterpret_cast<uintptr_t>(rays_copy)) & 15) == 0;
+    const bool x_double = (pk.in_chunks == 1);
+    const uint32_t x_lo_off = (uint32_t)(2 * pk.in_chunks * KSTEP_BYTES);  // lo half follows the hi k-steps
     for (long long j = 0; j < n_iters; ++j) {
-      const uint32_t xb = (uint32_t)(j & 1);
-      if (j >= 1) mbar_wait(bar(BAR_XFREE + xb), (uint32_t)(((j - 1) >> 1) & 1));
+      const uint32_t xb = x_double ? (uint32_t)(j & 1) : 0u;
+      // buffer xb was released once per two tiles (two buffers) / once per tile (one buffer)
+      if (j >= 1) mbar_wait(bar(BAR_XFREE + xb), x_double ? (uint32_t)(((j - 1) >> 1) & 1) : (uint32_t)((j - 1) & 1));
       uint8_t* xhi = smem + OFF_X + xb * X_BUF_BYTES;
       const long long tile = j * gridDim.x + blockIdx.x;
       for (int r = et; r < BM; r += 32 * ENC_WARPS) {
@@ -307,7 +324,7 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
           const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
           const uint32_t off = (uint32_t)(k >> 4) * KSTEP_BYTES + ks_slot(r, (k >> 3) & 1) + (uint32_t)(k & 7) * 2u;
           *reinterpret_cast<__nv_bfloat16*>(xhi + off) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(xhi + 2 * KSTEP_BYTES + off) = lo;
+          *reinterpret_cast<__nv_bfloat16*>(xhi + x_lo_off + off) = lo;
         };
         const long long ray = tile * BM + r;
         if (ray < n_rays) {
@@ -403,71 +420,38 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
           const int nslice = (P.n + 15) / 16;
           const int last_h = (grp < nslice) ? ((nslice - 1 - grp) / EPI_GROUPS) * EPI_GROUPS + grp : -1;
           if (last_h < 0) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
-          if (use_tma_store) {
-            for (int h = grp; h < nslice; h += EPI_GROUPS) {
-              uint32_t v[16];
-              tmem_ld16(t_addr + h * 16, v);
-              if (h == last_h) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
-              const float4* b4 = reinterpret_cast<const float4*>(bias + h * 16);
-              const uint32_t stg_s = sbase + stg_off + box * 2048;
-              box = (box + 1) & (STG_BOXES - 1);
-              // the store issued STG_BOXES boxes ago must have been read out of this box
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
-              __syncwarp();
+          for (int h = grp; h < nslice; h += EPI_GROUPS) {
+            uint32_t v[16];
+            tmem_ld16(t_addr + h * 16, v);
+            if (h == last_h) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
+            const float4* b4 = reinterpret_cast<const float4*>(bias + h * 16);
+            const uint32_t stg_s = sbase + stg_off + box * 2048;
+            box = (box + 1) & (STG_BOXES - 1);
+            // the store issued STG_BOXES boxes ago must have been read out of this box
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+            __syncwarp();
 #pragma unroll
-              for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 b = b4[i4];
-                float4 o;
-                o.x = __uint_as_float(v[i4 * 4 + 0]) + b.x;
-                o.y = __uint_as_float(v[i4 * 4 + 1]) + b.y;
-                o.z = __uint_as_float(v[i4 * 4 + 2]) + b.z;
-                o.w = __uint_as_float(v[i4 * 4 + 3]) + b.w;
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_s + lane * 64 + i4 * 16), "f"(o.x), "f"(o.y),
-                             "f"(o.z), "f"(o.w)
-                             : "memory");
-              }
-              fence_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                const int x = P.out_col0 + h * 16;
-                const int y = (int)(tile * BM + (warp & 3) * 32);
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                                 reinterpret_cast<uint64_t>(&heads_map)),
-                             "r"(x), "r"(y), "r"(stg_s)
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              }
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 b = b4[i4];
+              float4 o;
+              o.x = __uint_as_float(v[i4 * 4 + 0]) + b.x;
+              o.y = __uint_as_float(v[i4 * 4 + 1]) + b.y;
+              o.z = __uint_as_float(v[i4 * 4 + 2]) + b.z;
+              o.w = __uint_as_float(v[i4 * 4 + 3]) + b.w;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_s + lane * 64 + i4 * 16), "f"(o.x), "f"(o.y),
+                           "f"(o.z), "f"(o.w)
+                           : "memory");
             }
-          } else {
-            // fallback when no tensor map is available: transpose through the staging box, two 64-byte row segments per store
-            float* stg = reinterpret_cast<float*>(smem + stg_off);
-            const int half = lane >> 4, cidx = lane & 15;
-            const long long row0 = tile * BM + (warp & 3) * 32;
-            for (int h = grp; h < nslice; h += EPI_GROUPS) {
-              uint32_t v[16];
-              tmem_ld16(t_addr + h * 16, v);
-              if (h == last_h) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
-              const float4* b4 = reinterpret_cast<const float4*>(bias + h * 16);
-              const int sw = (lane >> 1) & 15;  // element i of row `lane` sits at (i ^ sw): conflict-free both ways
-#pragma unroll
-              for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 b = b4[i4];
-                stg[lane * 16 + ((i4 * 4 + 0) ^ sw)] = __uint_as_float(v[i4 * 4 + 0]) + b.x;
-                stg[lane * 16 + ((i4 * 4 + 1) ^ sw)] = __uint_as_float(v[i4 * 4 + 1]) + b.y;
-                stg[lane * 16 + ((i4 * 4 + 2) ^ sw)] = __uint_as_float(v[i4 * 4 + 2]) + b.z;
-                stg[lane * 16 + ((i4 * 4 + 3) ^ sw)] = __uint_as_float(v[i4 * 4 + 3]) + b.w;
-              }
-              __syncwarp();
-              const int col = P.out_col0 + h * 16 + cidx;
-              const bool col_ok = (h * 16 + cidx < P.n) && (col < cfg.mlp_out);
-              float* dst = heads + (row0 + half) * (long long)cfg.mlp_out + col;
-#pragma unroll
-              for (int rr = 0; rr < 32; rr += 2) {
-                const int r = rr + half;
-                const float o = stg[r * 16 + (cidx ^ ((r >> 1) & 15))];
-                if (col_ok && row0 + r < n_rays) dst[(long long)rr * cfg.mlp_out] = o;
-              }
-              __syncwarp();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int x = P.out_col0 + h * 16;
+              const int y = (int)(tile * BM + (warp & 3) * 32);
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                               reinterpret_cast<uint64_t>(&heads_map)),
+                           "r"(x), "r"(y), "r"(stg_s)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
         }
@@ -491,29 +475,34 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
   }
 }
 
-// Pass table + weight images for the half-pass layout.  Same image format as hr_mlp_tc.cu (pack_tc_pass), N = 128.
-int pack_mlp_tc2(hr_handle* h, const hr_params*, const float* const* w_dev, const float* const* b_dev, cudaStream_t st) {
+// Pass table + weight images (format: hr_tc_pack.cu).  Called by hr_upload with the handle's device current.
+int pack_mlp_tc2(hr_handle* h, const float* const* w_dev, const float* const* b_dev, cudaStream_t st) {
   const hr_config& c = h->cfg;
   MlpTcPack& pk = h->tc;
-  memset(&pk, 0, sizeof(pk));
-  pk.version = 2;
-  if (c.mlp_width != 256) return hr_fail("tensor-core sample net: width must be 256");
-  if (c.mlp_in > 32) return hr_fail("tensor-core sample net: encoded input wider than 32");
+  const int W = c.mlp_width;
+  if (W != 128 && W != 256) return hr_fail("tensor-core sample net: hidden width must be 128 or 256 (got %d)", W);
+  if (c.mlp_in > 64) return hr_fail("tensor-core sample net: encoded input wider than 64 features (%d)", c.mlp_in);
+  const int in_chunks = (c.mlp_in + 31) / 32;
   const int L = c.mlp_layers;
+  // the layout is a pure function of the config: when a pack of the same layout exists only its contents are rewritten
+  // (no cudaFree / cudaMalloc on a parameter refresh -- needed once per optimiser step by the training path)
+  MlpTcPack np_{};
+  np_.in_chunks = in_chunks;
   int np = 0, bias_off = 0;
   size_t bytes = 0;
   for (int l = 0; l < L; ++l) {
     const bool last = (l == L - 1);
-    const int out = last ? c.mlp_out : 256;
+    const int out = last ? c.mlp_out : W;
     const int n_parts = (out + 127) / 128;
     for (int part = 0; part < n_parts; ++part) {
       if (np >= HR_TC_MAX_PASSES) return hr_fail("tensor-core sample net: too many passes (%d output columns)", c.mlp_out);
-      TcPass& P = pk.passes[np++];
+      TcPass& P = np_.passes[np++];
       const int rem = out - part * 128;
+      const bool reads_input = (l == 0 || l == c.mlp_skip);
       P.layer = l;
       P.n = rem >= 128 ? 128 : (rem + 15) / 16 * 16;
-      P.first_chunk = (l == 0 || l == c.mlp_skip) ? 0 : 1;
-      P.n_chunks = (l == 0) ? 1 : (l == c.mlp_skip ? 9 : 8);
+      P.first_chunk = reads_input ? 0 : in_chunks;
+      P.n_chunks = (l == 0) ? in_chunks : (W / 32 + (reads_input ? in_chunks : 0));
       P.bias_off = bias_off;
       P.is_final = last ? 1 : 0;
       P.out_col0 = part * 128;
@@ -523,59 +512,79 @@ int pack_mlp_tc2(hr_handle* h, const hr_params*, const float* const* w_dev, cons
     }
   }
   if (bias_off > tc2::BIAS_FLOATS) return hr_fail("tensor-core sample net: bias table too large");
-  pk.n_passes = np;
-  pk.bias_count = bias_off;
-  uint8_t* wp = nullptr;
-  float* bp = nullptr;
-  cudaError_t e = cudaMalloc((void**)&wp, bytes);
-  if (e != cudaSuccess) return hr_fail("cudaMalloc(tc weights %zu): %s", bytes, cudaGetErrorString(e));
-  h->owned.push_back(wp);
-  e = cudaMalloc((void**)&bp, (size_t)bias_off * sizeof(float));
-  if (e != cudaSuccess) return hr_fail("cudaMalloc(tc bias): %s", cudaGetErrorString(e));
-  h->owned.push_back(bp);
+  np_.n_passes = np;
+  np_.bias_count = bias_off;
+  np_.wpack_bytes = (long long)bytes;
+  if (h->tc_alloc_bytes != bytes || h->tc_alloc_bias != bias_off || !pk.wpack) {
+    if (pk.wpack) cudaFree(const_cast<void*>(pk.wpack));
+    if (pk.bias) cudaFree(const_cast<float*>(pk.bias));
+    pk.wpack = nullptr; pk.bias = nullptr;
+    h->tc_alloc_bytes = 0; h->tc_alloc_bias = 0;
+    void* wp = nullptr; float* bp = nullptr;
+    cudaError_t e = cudaMalloc(&wp, bytes);
+    if (e != cudaSuccess) return hr_fail("cudaMalloc(tc weights %zu): %s", bytes, cudaGetErrorString(e));
+    e = cudaMalloc((void**)&bp, (size_t)bias_off * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(wp); return hr_fail("cudaMalloc(tc bias): %s", cudaGetErrorString(e)); }
+    np_.wpack = wp; np_.bias = bp;
+    h->tc_alloc_bytes = bytes; h->tc_alloc_bias = bias_off;
+    // opt in to the 219 KB of dynamic shared memory once per (handle, device)
+    e = cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
+    if (e != cudaSuccess) return hr_fail("cudaFuncSetAttribute(mlp_tc2_kernel): %s", cudaGetErrorString(e));
+    // the TMA descriptor encoder comes from the driver through the runtime (no link-time libcuda dependency)
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      h->tma_encode = fn;
+    if (!h->tma_encode) return hr_fail("cuTensorMapEncodeTiled is not available from this driver");
+  } else {
+    np_.wpack = pk.wpack; np_.bias = pk.bias;
+  }
+  pk = np_;
+  uint8_t* wp = (uint8_t*)const_cast<void*>(pk.wpack);
+  float* bp = const_cast<float*>(pk.bias);
   size_t off = 0;
   for (int p = 0; p < np; ++p) {
     const TcPass& P = pk.passes[p];
     const int l = P.layer;
     const bool last = (l == L - 1), skip = (l == c.mlp_skip), first = (l == 0);
-    const int in_src = first ? c.mlp_in : (skip ? c.mlp_in + 256 : 256);
+    const int in_src = first ? c.mlp_in : (skip ? c.mlp_in + W : W);
     launch_pack_tc_pass(w_dev[l], b_dev[l], wp + off, bp + P.bias_off, P.n, P.first_chunk, P.n_chunks, in_src, c.mlp_in,
-                        skip ? 1 : 0, last ? c.mlp_out : 256, last ? c.n_samples : 0, c.head_stride, P.out_col0, st);
+                        skip ? 1 : 0, in_chunks, last ? c.mlp_out : W, last ? c.n_samples : 0, c.head_stride, P.out_col0, st);
     off += (size_t)P.n_chunks * 2 * P.n * 64;
   }
-  e = cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return hr_fail("tc pack launch failed: %s", cudaGetErrorString(e));
-  pk.wpack = wp;
-  pk.bias = bp;
-  pk.wpack_bytes = (long long)bytes;
   return 0;
 }
 
-cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, const float* rays, float* heads, long long n, int num_sms,
-                           cudaStream_t stream, float* rays_copy) {
+void free_mlp_tc2(hr_handle* h) {
+  if (h->tc.wpack) cudaFree(const_cast<void*>(h->tc.wpack));
+  if (h->tc.bias) cudaFree(const_cast<float*>(h->tc.bias));
+  h->tc.wpack = nullptr; h->tc.bias = nullptr;
+  h->tc_alloc_bytes = 0; h->tc_alloc_bias = 0;
+}
+
+cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, void* tma_encode, const float* rays, float* heads,
+                           long long n, int num_sms, cudaStream_t stream, float* rays_copy) {
   unsigned long long* trace = nullptr;
+  int trace_iter = 1;
+#ifdef HR_DIAG
   const bool want_trace = getenv("HR_TC_TRACE") != nullptr;
   if (want_trace) {
     cudaMalloc((void**)&trace, 1024 * sizeof(unsigned long long));
     cudaMemset(trace, 0, 1024 * sizeof(unsigned long long));
+    if (getenv("HR_TC_TRACE_ITER")) trace_iter = atoi(getenv("HR_TC_TRACE_ITER"));
   }
+#endif
   long long tiles = (n + tc::BM - 1) / tc::BM;
   int grid = (int)(tiles < num_sms ? tiles : num_sms);
   if (grid < 1) grid = 1;
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
   CUtensorMap hmap;
-  static const int want_tma = getenv("HR_TC_TMA_STORE") ? atoi(getenv("HR_TC_TMA_STORE")) : 1;
-  const int use_tma = (want_tma && make_heads_map(&hmap, heads, cfg.mlp_out, n, 16, false)) ? 1 : 0;
-  mlp_tc2_kernel<<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, stream>>>(cfg, pk, rays, heads, n, trace, hmap, use_tma, rays_copy,
-                                                                    getenv("HR_TC_TRACE_ITER") ? atoi(getenv("HR_TC_TRACE_ITER")) : 1);
+  if (!make_heads_map(&hmap, tma_encode, heads, cfg.mlp_out, n, 16)) return cudaErrorInvalidValue;
+  mlp_tc2_kernel<<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, stream>>>(cfg, pk, rays, heads, n, trace, hmap, rays_copy, trace_iter);
   cudaError_t le = cudaGetLastError();
+#ifdef HR_DIAG
   if (want_trace) {
     unsigned long long hbuf[1024];
     cudaStreamSynchronize(stream);
@@ -604,6 +613,7 @@ cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, const floa
     fprintf(stderr, "[tc2-trace] CTAs: first start 0, last start %lld ns, first end %lld ns, last end %lld ns; CTA0 %lld..%lld ns; mean SM clock %.0f MHz\n",
             (long long)(s1 - s0), (long long)(e0 - s0), (long long)(e1 - s0), (long long)(hbuf[256] - s0), (long long)(hbuf[257] - s0), mhz);
   }
+#endif
   return le;
 }
 

@@ -11,8 +11,6 @@
 //     LDG.128 (reference: F.grid_sample calls in nlf/nets/tensorf_dynamic.py:287-371 and
 //     nlf/nets/tensorf_no_sample.py:47-126).
 // Nothing per-sample ever goes to HBM: rays (4*c_in B) + sample-net heads in, rgb (12 B) out.
-#include <cstdlib>
-
 #include "hr_common.cuh"
 
 namespace hr {
@@ -193,11 +191,11 @@ __device__ __forceinline__ void group_products(const GroupTaps<C, DYN>& g, float
   for (int c = 0; c < 4; ++c) prod[c] = A[c] * B[c];
 }
 
-template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool STAGES>
+template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool EXTRA>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (C1 + C2 == 0 || SPL == 1) ? 3 : 2)
 render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Derived dv,
               const __grid_constant__ RenderTabs tabs, const float* __restrict__ rays,
-              const float* __restrict__ heads, float* __restrict__ rgb_out, long long n_rays, StageOut so,
+              const float* __restrict__ heads, float* __restrict__ rgb_out, long long n_rays, ExtraOut so,
               unsigned char* __restrict__ rgb8_out) {
   constexpr int NT = C0 + C1 + C2;
   constexpr int ROWS = (SHADE == HR_SHADE_SH) ? 9 : 1;
@@ -237,10 +235,6 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     for (int i = 0; i < NT; ++i) G[i] = s_basis[qc * NT + fcol[i]];
   }
 
-  // Programmatic dependent launch: everything above overlaps the tail of the sample-net kernel; its heads become
-  // visible here.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-
   const float inv_x = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[3], cfg.aabb[0]));  // invaabbSize (tensorf_base.py:292)
   const float inv_y = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[4], cfg.aabb[1]));
   const float inv_z = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[5], cfg.aabb[2]));
@@ -279,13 +273,13 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     }
 
     // ---- per-ray keyframe snap (utils/flow_utils.py:18-31), time coordinate and keyframe row ----
-    float toff = 0.0f;
+    float toff = 0.0f, base_t = 0.0f;
     int krow = 0;  // keyframe index: the time coordinate of every sample of this ray depends only on it
     if (DYN || cfg.use_flow) {
       float tt = __fmul_rn(time, dv.time_fac);
       tt = fminf(fmaxf(tt, 0.0f), dv.kf_max);
       tt = rintf(__fsub_rn(tt, 1e-5f));
-      const float base_t = __fmul_rn(tt, dv.time_inv_fac);
+      base_t = __fmul_rn(tt, dv.time_inv_fac);
       toff = __fsub_rn(time, base_t);
       if (DYN) krow = max(0, min((int)tt, dv.kt - 1));
     }
@@ -452,6 +446,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     float dist[SPL], fx[SPL], fy[SPL], fz[SPL];
     int ix[SPL], iy[SPL], iz[SPL];  // ix < 0 flags an invalid sample
     bool valid[SPL];
+    float pts[EXTRA ? SPL : 1][3];  // final sample points, kept only by the variant that reports them
     float cocx = ox, cocy = oy, cocz = oz;
     if (cfg.contract_type == HR_CONTRACT_MIPNERF) contract_point(cfg, dv, cocx, cocy, cocz);
     else if (cfg.contract_type == HR_CONTRACT_AFFINE) contract_point_affine(cfg, cocx, cocy, cocz);
@@ -495,7 +490,8 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       fy[j] = ty - (float)iy[j];
       fz[j] = tz - (float)iz[j];
       if (!valid[j]) ix[j] = -1;
-      if (STAGES && act) {
+      if (EXTRA) { pts[j][0] = px; pts[j][1] = py; pts[j][2] = pz; }
+      if (EXTRA && act) {
         if (so.distances) so.distances[ray * S + s] = t;
         if (so.points) {
           so.points[(ray * S + s) * 3 + 0] = px;
@@ -646,7 +642,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       carryT = carryT * __shfl_sync(kFull, inc, 31);
       const float w = alpha * T;
       wgt[j] = w;
-      if (STAGES && s < S) {
+      if (EXTRA && s < S) {
         if (so.sigma) so.sigma[ray * S + s] = sigma;
         if (so.weights) so.weights[ray * S + s] = w;
       }
@@ -658,6 +654,65 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         const float cshv = cfg.use_color_scale_shift ? apply_act(cfg.act_cshift, csh_raw[c]) : 0.0f;
         csA[j][c] = (s < S) ? m * (csv + 1.0f) : 0.0f;
         accB[c] += (s < S) ? w * cshv : 0.0f;
+      }
+      if constexpr (EXTRA) {
+        // ---- extra fields (tensorf_dynamic.py:808-837): sum_s w_s x_s, sum_s pred_w_s x_s, or x itself ----
+        // pred_weights = alpha2weights(x['weights'][..., 0]) with x['weights'] == 1 (base.py:183-191):
+        // T_s = prod_{k<s} (1 - 1 + 1e-10), pred_w_s = 1 * T_s
+        float pw = 1.0f;
+        for (int k = 0; k < min(s, 8); ++k) pw = __fmul_rn(pw, __fadd_rn(__fsub_rn(1.0f, 1.0f), 1e-10f));
+#pragma unroll 1
+        for (int f = 0; f < HR_N_FIELDS; ++f) {
+          float* fo = so.field_out[f];
+          if (fo == nullptr) continue;  // warp-uniform
+          const int mode = so.field_mode[f];
+          // per-sample heads are x[name] = activation(raw) (ray.py:333-337); the other keys are built-ins of the pipeline
+          int dim = 1, hoff = -1;
+          const hr_act* hact = &cfg.act_z;
+          switch (f) {
+            case HR_FIELD_POINTS: case HR_FIELD_VIEWDIRS: dim = 3; break;
+            case HR_FIELD_SPATIAL_FLOW: dim = 3; hoff = cfg.off_flow; hact = &cfg.act_flow; break;
+            case HR_FIELD_SIGMA: hoff = cfg.off_sigma; hact = &cfg.act_sigma; break;
+            case HR_FIELD_POINT_SIGMA: hoff = cfg.off_point_sigma; hact = &cfg.act_point_sigma; break;
+            case HR_FIELD_POINT_OFFSET: dim = 3; hoff = cfg.off_offset; hact = &cfg.act_offset; break;
+            case HR_FIELD_COLOR_SCALE: dim = 3; hoff = cfg.off_cscale; hact = &cfg.act_cscale; break;
+            case HR_FIELD_COLOR_SHIFT: dim = 3; hoff = cfg.off_cshift; hact = &cfg.act_cshift; break;
+            default: break;
+          }
+          for (int c = 0; c < dim; ++c) {
+            float v;
+            if (hoff >= 0) {
+              v = apply_act(*hact, __ldg(hp + (long long)(hoff + c) * S));
+              // two embeddings write their result back under the head's name:
+              //   AdvectPoints: x['spatial_flow'] = spatial_flow_activation(x['spatial_flow'])        (point.py:815-817)
+              //   PointOffset : x['point_offset'] = activation(x['point_offset']) * (1 - sigma)        (point.py:383-389)
+              if (f == HR_FIELD_SPATIAL_FLOW && cfg.use_flow) v = apply_act(cfg.flow_act, v);
+              if (f == HR_FIELD_POINT_OFFSET && cfg.use_offset) v = hof[j][c];
+            } else {
+              switch (f) {
+                case HR_FIELD_POINTS: v = pts[j][c]; break;
+                case HR_FIELD_DISTANCES: v = dist[j]; break;
+                case HR_FIELD_BASE_TIMES: v = base_t; break;
+                case HR_FIELD_TIME_OFFSET: v = toff; break;
+                case HR_FIELD_TIMES: v = time; break;
+                case HR_FIELD_VIEWDIRS: v = (c == 0) ? dx : ((c == 1) ? dy : dz); break;
+                default: v = 1.0f; break;  // HR_FIELD_WEIGHTS
+              }
+            }
+            if (mode == HR_FIELD_NO_OVER) {
+              if (s < S) fo[(ray * S + s) * dim + c] = v;
+            } else {
+              float acc = (s < S) ? __fmul_rn((mode == HR_FIELD_PRED_WEIGHTS) ? pw : w, v) : 0.0f;
+#pragma unroll
+              for (int d = 1; d < 32; d <<= 1) acc += __shfl_xor_sync(kFull, acc, d);
+              // SPL registers per lane: partial sums of the rounds are added in round order by lane 0
+              if (lane == 0) {
+                float* dst = fo + ray * dim + c;
+                *dst = (j == 0) ? acc : (*dst + acc);
+              }
+            }
+          }
+        }
       }
     }
 
@@ -673,6 +728,13 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       const float g2 = __shfl_sync(kFull, csA[j][2], src);
       const float Aq = (q == 0) ? g0 : ((q == 1) ? g1 : g2);
       accq = fmaf(Aq, rgb_r[rd], accq);
+      if constexpr (EXTRA) {
+        if (so.rgb_samples != nullptr) {
+          const float ws = __shfl_sync(kFull, wgt[j], src);
+          const int sidx = j * 32 + src;
+          if (q < 3 && sidx < S) so.rgb_samples[(ray * S + sidx) * 3 + q] = (ws > cfg.weight_thre) ? rgb_r[rd] : 0.0f;
+        }
+      }
     }
 #pragma unroll
     for (int d = 4; d < 32; d <<= 1) accq += __shfl_xor_sync(kFull, accq, d);
@@ -705,7 +767,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
 
 template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE>
 static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
-                              const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
+                              const float* heads, float* rgb, long long n, const ExtraOut* so, int num_sms,
                               cudaStream_t stream, unsigned char* rgb8) {
   constexpr int ROWS = (SHADE == HR_SHADE_SH) ? 9 : 1;
   constexpr int NT = C0 + C1 + C2;
@@ -713,27 +775,19 @@ static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const Ren
   long long ctas_needed = (n + kWarpsPerCta - 1) / kWarpsPerCta;
   long long grid = ctas_needed < (long long)num_sms * kMinCtasPerSm * 2 ? ctas_needed : (long long)num_sms * kMinCtasPerSm * 2;
   if (grid < 1) grid = 1;
-  cudaLaunchConfig_t lc{};
-  lc.gridDim = dim3((unsigned)grid);
-  lc.blockDim = dim3(kWarpsPerCta * 32);
-  lc.dynamicSmemBytes = smem;
-  lc.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // may start while the sample-net kernel drains
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  lc.attrs = at;
-  static const int use_pdl = getenv("HR_PDL") ? atoi(getenv("HR_PDL")) : 0;  // measured: no gain on B200 (profiles/r1_notes.md)
-  lc.numAttrs = use_pdl ? 1 : 0;
+  const dim3 g((unsigned)grid), b(kWarpsPerCta * 32);
   if (so) {
-    return cudaLaunchKernelEx(&lc, render_kernel<SPL, DYN, C0, C1, C2, SHADE, true>, cfg, dv, tabs, rays, heads, rgb, n, *so, rgb8);
+    render_kernel<SPL, DYN, C0, C1, C2, SHADE, true><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, *so, rgb8);
+    return cudaGetLastError();
   }
-  StageOut none{nullptr, nullptr, nullptr, nullptr};
-  return cudaLaunchKernelEx(&lc, render_kernel<SPL, DYN, C0, C1, C2, SHADE, false>, cfg, dv, tabs, rays, heads, rgb, n, none, rgb8);
+  ExtraOut none{};
+  render_kernel<SPL, DYN, C0, C1, C2, SHADE, false><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, none, rgb8);
+  return cudaGetLastError();
 }
 
 template <int SPL, bool DYN, int C0, int C1, int C2>
 static cudaError_t launch_shade(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
-                                const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
+                                const float* heads, float* rgb, long long n, const ExtraOut* so, int num_sms,
                                 cudaStream_t stream, unsigned char* rgb8) {
   if (cfg.shading == HR_SHADE_SH)
     return launch_one<SPL, DYN, C0, C1, C2, HR_SHADE_SH>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
@@ -742,7 +796,7 @@ static cudaError_t launch_shade(const hr_config& cfg, const Derived& dv, const R
 
 template <int SPL, bool DYN>
 static cudaError_t launch_comps(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
-                                const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
+                                const float* heads, float* rgb, long long n, const ExtraOut* so, int num_sms,
                                 cudaStream_t stream, unsigned char* rgb8) {
   const int c0 = cfg.n_sigma[0], c1 = cfg.n_sigma[1], c2 = cfg.n_sigma[2];
   if (c0 == 8 && c1 == 0 && c2 == 0)
@@ -756,7 +810,7 @@ static cudaError_t launch_comps(const hr_config& cfg, const Derived& dv, const R
 
 // Entry used by hr_api.cu.  Returns cudaErrorInvalidValue for an unsupported component layout.
 cudaError_t launch_render(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
-                          const float* heads, float* rgb, long long n, const StageOut* so, int num_sms,
+                          const float* heads, float* rgb, long long n, const ExtraOut* so, int num_sms,
                           cudaStream_t stream, unsigned char* rgb8) {
   const bool two = cfg.n_samples > 32;
   if (cfg.dynamic) {

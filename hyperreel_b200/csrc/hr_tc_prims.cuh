@@ -151,9 +151,9 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 }  // namespace tc
 
-// host helpers defined in hr_mlp_tc.cu
-bool make_heads_map(CUtensorMap* hmap, const float* heads, int mlp_out, long long n, int box_cols, bool swizzle128);
+// host helpers defined in hr_tc_pack.cu
+bool make_heads_map(CUtensorMap* hmap, void* encode_fn, const float* heads, int mlp_out, long long n, int box_cols);
 void launch_pack_tc_pass(const float* W, const float* b, uint8_t* dst, float* bias_dst, int n, int first_chunk, int n_chunks,
-                         int in_src, int mlp_in, int is_skip, int out_rows, int perm_S, int perm_stride, int out_col0,
-                         cudaStream_t st);
+                         int in_src, int mlp_in, int is_skip, int in_chunks, int out_rows, int perm_S, int perm_stride,
+                         int out_col0, cudaStream_t st);
 }  // namespace hr

@@ -11,7 +11,7 @@ import os
 import subprocess
 import threading
 
-HR_ABI_VERSION = 6
+HR_ABI_VERSION = 7
 HR_MAX_GROUPS = 4
 HR_MAX_LAYERS = 10
 HR_MAX_SAMPLES = 64
@@ -23,6 +23,10 @@ CONTRACT_NONE, CONTRACT_MIPNERF, CONTRACT_AFFINE = 0, 1, 2
 SHADE_SH, SHADE_RGB = 0, 1
 DENSE_RELU, DENSE_SOFTPLUS, DENSE_RELU_ABS = 0, 1, 2
 MLP_FP32_SIMT, MLP_BF16X3_TC = 0, 1
+# extra fields of the colour net (hr_render_fields): key of the reference's dict `x` -> HR_FIELD_* id
+FIELDS = {"points": 0, "distances": 1, "base_times": 2, "time_offset": 3, "times": 4, "viewdirs": 5, "weights": 6,
+          "color_scale": 7, "color_shift": 8, "spatial_flow": 9, "sigma": 10, "point_sigma": 11, "point_offset": 12}
+FIELD_OVER, FIELD_NO_OVER, FIELD_PRED_WEIGHTS = 0, 1, 2
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libhyperreel_b200.so")
@@ -88,6 +92,10 @@ class hr_params(C.Structure):
     ]
 
 
+class hr_field_request(C.Structure):
+    _fields_ = [("field", C.c_int32), ("mode", C.c_int32), ("out", C.c_void_p)]
+
+
 class hr_camera(C.Structure):
     _fields_ = [
         ("c2w", C.c_float * 12), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
@@ -106,7 +114,9 @@ EXPORTS = {
     "hr_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
     "hr_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hr_render_stages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hr_render_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(hr_field_request),
+                                    C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "hr_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "hr_generate_rays": (C.c_int, [C.POINTER(hr_camera), C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "hr_render_to8b": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

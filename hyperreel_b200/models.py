@@ -43,17 +43,27 @@ def _dataset_facts(system) -> dict:
     return ds
 
 
+def resolve_mlp_mode(name: str) -> int:
+    """'auto' (default) and 'bf16x3' select the tcgen05 sample net -- every pipeline the fused path accepts runs on it
+    (hidden width 128 / 256, encoded input <= 64 features); 'fp32' selects the CUDA-core kernel, the parity anchor."""
+    try:
+        return {"auto": L.MLP_BF16X3_TC, "bf16x3": L.MLP_BF16X3_TC, "fp32": L.MLP_FP32_SIMT}[name]
+    except KeyError:
+        raise ValueError(f"mlp_mode must be 'auto', 'bf16x3' or 'fp32', got {name!r}") from None
+
+
 class LightfieldModel(nn.Module):
     def __init__(self, cfg, **kwargs):
         super().__init__()
-        dataset = kwargs.get("dataset") or _dataset_facts(kwargs.get("system"))
+        dataset = dict(kwargs.get("dataset") or _dataset_facts(kwargs.get("system")))  # never mutate the caller's dict
         dataset.setdefault("near", 0.0)
         dataset.setdefault("far", 1.0)
         dataset.setdefault("depth_range", [dataset["near"], dataset["far"]])
-        mode = {"fp32": L.MLP_FP32_SIMT, "bf16x3": L.MLP_BF16X3_TC}[kwargs.get("mlp_mode", "fp32")]
+        self._mlp_mode = resolve_mlp_mode(kwargs.get("mlp_mode", "auto"))
+        self._iters_per_epoch = kwargs.get("iters_per_epoch")
         self.cfg = cfg
         self.sig: Signature = lower(cfg, dataset, cur_iter=RENDER_ITER,
-                                    iters_per_epoch=kwargs.get("iters_per_epoch"), mlp_mode=mode)
+                                    iters_per_epoch=self._iters_per_epoch, mlp_mode=self._mlp_mode)
         self.num_outputs = 3
         self.cur_iter = RENDER_ITER
         grid = kwargs.get("grid") or default_grid(self.sig)
@@ -72,7 +82,17 @@ class LightfieldModel(nn.Module):
         """The fused path implements render-time semantics only (all PE windows open, EaseValue elapsed);
         the reference sets iteration 1e7*iters when rendering (nlf/__init__.py:582-583)."""
         self.cur_iter = i
-        lower(self.cfg, self.sig.dataset, cur_iter=int(i))  # raises UnsupportedPipeline if a window is still open
+        # Re-lower at iteration i with the same epoch scale and net mode.  Raises UnsupportedPipeline while a PE / EaseValue
+        # window is still open; a different graph at i (an embedding gated by wait/stop_iters, mask.stop_iters) must not be
+        # rendered with the construction-time semantics: adopt it and rebuild the native handle.
+        new = lower(self.cfg, self.sig.dataset, cur_iter=int(i), iters_per_epoch=self._iters_per_epoch, mlp_mode=self._mlp_mode)
+        for k in range(6):
+            new.cfg.aabb[k] = self.sig.cfg.aabb[k]  # aabb is checkpoint state, kept in sync by _ensure_uploaded
+        if bytes(new.cfg) != bytes(self.sig.cfg):
+            if new.mlp_layer_shapes != self.sig.mlp_layer_shapes or list(new.cfg.n_sigma) != list(self.sig.cfg.n_sigma):
+                raise UnsupportedPipeline("set_iter: the pipeline at this iteration has different parameter shapes")
+            self.sig = new
+            self._release_handle()
         self.color_model.set_iter(i)
 
     def forward(self, rays: torch.Tensor, render_kwargs: Optional[Dict] = None) -> Dict[str, torch.Tensor]:
@@ -91,28 +111,74 @@ class LightfieldModel(nn.Module):
         if not fields:
             L.check(self._lib.hr_render(self._handle, rays.data_ptr(), n, rgb.data_ptr(), ws.data_ptr(), ws.numel(), stream))
             return {"rgb": rgb}
-        # extra composited fields (tensorf_dynamic.py:813-837): weights -> 'render_weights', depth = sum w * distances
-        S = self.sig.n_samples
-        dist = torch.empty((n, S), device=rays.device)
-        wts = torch.empty((n, S), device=rays.device)
-        L.check(self._lib.hr_render_stages(self._handle, rays.data_ptr(), n, rgb.data_ptr(), None, dist.data_ptr(),
-                                           None, None, wts.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        # extra outputs (tensorf_dynamic.py:808-837 / tensorf_no_sample.py:254-278): reduced in the render kernel's epilogue
+        no_over = set(render_kwargs.get("no_over_fields", []))
+        pred_w = set(render_kwargs.get("pred_weights_fields", []))
         out = {"rgb": rgb}
+        rw_ptr = None
+        reqs = []
         for key in fields:
             if key == "render_weights":
-                out[key] = wts
-            elif key == "distances":
-                out[key] = (wts * dist).sum(-1, keepdim=True)
-            else:
-                raise UnsupportedPipeline(f"field '{key}' is not produced by the fused path")
+                out[key] = torch.empty((n, self.sig.n_samples), device=rays.device)
+                rw_ptr = out[key].data_ptr()
+                continue
+            mode = L.FIELD_NO_OVER if key in no_over else (L.FIELD_PRED_WEIGHTS if key in pred_w else L.FIELD_OVER)
+            fid, dim = self._field(key)
+            out[key] = torch.empty((n, (self.sig.n_samples if mode == L.FIELD_NO_OVER else 1) * dim), device=rays.device)
+            reqs.append(L.hr_field_request(fid, mode, out[key].data_ptr()))
+        arr = (L.hr_field_request * max(len(reqs), 1))(*reqs)
+        L.check(self._lib.hr_render_fields(self._handle, rays.data_ptr(), n, rgb.data_ptr(), rw_ptr, arr, len(reqs),
+                                           ws.data_ptr(), ws.numel(), stream))
         return out
 
     def embed(self, rays: torch.Tensor, render_kwargs: Optional[Dict] = None) -> Dict[str, torch.Tensor]:
-        """Per-sample outputs of the embedding pipeline, flattened per ray like RayPointEmbedding.forward
-        (nlf/embedding/embedding.py:112-114): 'points' [N, 3S], 'distances' [N, S]."""
-        st = self.render_stages(rays)
-        n = st["points"].shape[0]
-        return {"points": st["points"].reshape(n, -1), "distances": st["distances"].reshape(n, -1)}
+        """What RayPointEmbedding.forward returns to ``render_fn.embed`` (nlf/embedding/embedding.py:100-117): every key
+        ``extract_fields`` lets through (its own list plus render_kwargs['fields'], nlf/embedding/point.py:236-244),
+        flattened to ``[N, S*dim]``."""
+        render_kwargs = render_kwargs or {}
+        rays = self._check_rays(rays)
+        n, S = rays.shape[0], self.sig.n_samples
+        keys = []
+        for key in list(self._extract_fields()) + list(render_kwargs.get("fields", [])):
+            if key in self._available_fields() and key not in keys:
+                keys.append(key)
+        out = {k: torch.empty((n, S * self._field(k)[1]), device=rays.device) for k in keys}
+        if n == 0:
+            return out
+        self._ensure_uploaded(rays.device)
+        ws = self._workspace(n, rays.device)
+        rgb = torch.empty((n, 3), device=rays.device)
+        reqs = [L.hr_field_request(self._field(k)[0], L.FIELD_NO_OVER, out[k].data_ptr()) for k in keys]
+        arr = (L.hr_field_request * max(len(reqs), 1))(*reqs)
+        stream = torch.cuda.current_stream(rays.device).cuda_stream
+        L.check(self._lib.hr_render_fields(self._handle, rays.data_ptr(), n, rgb.data_ptr(), None, arr, len(reqs),
+                                           ws.data_ptr(), ws.numel(), stream))
+        return out
+
+    # ------------------------------------------------------------------ the dict `x` of the reference, by name
+    def _extract_fields(self):
+        embs = self.sig.model_cfg.embedding.embeddings
+        return list(next(e for e in embs.values() if e.type == "extract_fields").fields)
+
+    def _available_fields(self):
+        """Keys of the reference's dict ``x`` when it reaches extract_fields, restricted to what the fused path carries."""
+        c = self.sig.cfg
+        have = {"points", "distances", "weights", "viewdirs"} | set(self.sig.head_names)
+        if c.dynamic or c.use_flow:
+            have |= {"base_times", "time_offset"}
+        embs = self.sig.model_cfg.embedding.embeddings
+        addp = next(e for e in embs.values() if e.type == "add_point_outputs")
+        if "times" in list(addp.extra_outputs):
+            have.add("times")
+        return {k for k in have if k in L.FIELDS}
+
+    def _field(self, key):
+        if key not in L.FIELDS:
+            raise UnsupportedPipeline(f"field '{key}' is not produced by the fused path")
+        if key not in self._available_fields():
+            raise KeyError(key)  # the reference fails the same way on x[key]
+        dims = {"points": 3, "viewdirs": 3, "color_scale": 3, "color_shift": 3, "spatial_flow": 3, "point_offset": 3}
+        return L.FIELDS[key], dims.get(key, 1)
 
     # ------------------------------------------------------------------ native plumbing
     def render_stages(self, rays: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -125,6 +191,7 @@ class LightfieldModel(nn.Module):
             "rgb": torch.empty((n, 3), device=dev), "mlp_out": torch.empty((n, c.mlp_out), device=dev),
             "distances": torch.empty((n, S), device=dev), "points": torch.empty((n, S, 3), device=dev),
             "sigma": torch.empty((n, S), device=dev), "weights": torch.empty((n, S), device=dev),
+            "rgb_samples": torch.empty((n, S, 3), device=dev),
         }
         if n == 0:
             return out
@@ -132,7 +199,8 @@ class LightfieldModel(nn.Module):
         stream = torch.cuda.current_stream(dev).cuda_stream
         L.check(self._lib.hr_render_stages(self._handle, rays.data_ptr(), n, out["rgb"].data_ptr(), out["mlp_out"].data_ptr(),
                                            out["distances"].data_ptr(), out["points"].data_ptr(), out["sigma"].data_ptr(),
-                                           out["weights"].data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                                           out["weights"].data_ptr(), out["rgb_samples"].data_ptr(), ws.data_ptr(), ws.numel(),
+                                           stream))
         return out
 
     def render_host(self, rays_host: torch.Tensor, rgb_host: Optional[torch.Tensor] = None, chunk: int = 0) -> torch.Tensor:
@@ -220,8 +288,20 @@ class LightfieldModel(nn.Module):
         sv = getattr(net, "struct_version", 0)
         ts = self._version_tensors
         if ts is None or ts[0] != sv:  # init_svd_volume (a resized grid) replaced the table Parameters
-            ts = self._version_tensors = (sv, list(self.parameters()) + [net.aabb, net.gridSize])
-        return tuple([(t._version, t.data_ptr()) for t in ts[1]])
+            ts = self._version_tensors = (sv, list(self.parameters()))
+        # the two buffers are read fresh on every call: Module.to()/.cuda() replaces buffer objects
+        return tuple([(t._version, t.data_ptr()) for t in ts[1] + [net.aabb, net.gridSize]])
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)  # .to() / .cuda() / .float(): Parameter storage may have moved
+        self.mark_dirty()
+        return out
+
+    def _release_handle(self):
+        if getattr(self, "_handle", None):
+            self._lib.hr_destroy(self._handle)
+        self._handle = C.c_void_p()
+        self._uploaded_version = None
 
     def _ensure_uploaded(self, dev: torch.device):
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -233,13 +313,9 @@ class LightfieldModel(nn.Module):
         if aabb != [float(self.sig.cfg.aabb[i]) for i in range(6)]:
             for i in range(6):
                 self.sig.cfg.aabb[i] = aabb[i]
-            if self._handle:
-                self._lib.hr_destroy(self._handle)
-                self._handle = C.c_void_p()
+            self._release_handle()
         if not self._handle or self._device_index != idx:
-            if self._handle:
-                self._lib.hr_destroy(self._handle)
-                self._handle = C.c_void_p()
+            self._release_handle()
             L.check(self._lib.hr_create(C.byref(self.sig.cfg), idx, C.byref(self._handle)))
             self._device_index = idx
             self._uploaded_version = None

@@ -97,7 +97,7 @@ class Signature:
 
 
 def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch: Optional[int] = None,
-          mlp_mode: int = L.MLP_FP32_SIMT) -> Signature:
+          mlp_mode: int = L.MLP_BF16X3_TC) -> Signature:
     """model cfg (reference schema) + dataset facts -> Signature / hr_config."""
     from .config import epochs_to_iters
 
@@ -240,6 +240,12 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     head_channels = [int(pred.outputs[k].channels) for k in head_names]
     stride = sum(head_channels)
     c.mlp_in, c.mlp_width, c.mlp_layers = mlp_in, int(ncfg.hidden_channels), depth
+    if c.mlp_width not in (128, 256):
+        raise UnsupportedPipeline(f"sample net hidden width {c.mlp_width} is not on the fused path (128 or 256)")
+    if mlp_in > 64:
+        raise UnsupportedPipeline(f"sample net input of {mlp_in} encoded features is not on the fused path (<= 64)")
+    if not (2 <= depth <= L.HR_MAX_LAYERS):
+        raise UnsupportedPipeline(f"sample net depth {depth} is not on the fused path")
     c.mlp_skip = int(skips[0]) if skips else -1
     c.mlp_out = S * stride
     c.leaky_slope = 0.01

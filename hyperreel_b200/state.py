@@ -137,8 +137,14 @@ def scale_density(sd: Dict[str, torch.Tensor], gain: float) -> Dict[str, torch.T
     return out
 
 
+def scale_appearance(sd: Dict[str, torch.Tensor], gain: float) -> Dict[str, torch.Tensor]:
+    """Scale both factors of every appearance table (planes and lines / time planes): the reference initialises them at
+    0.1 * N(0,1), so their products barely move the shaded colour; trained scenes have O(1) features."""
+    return {k: (v * gain if ".app_" in k else v) for k, v in sd.items()}
+
+
 def seeded_state_dict(sig: Signature, grid: Optional[Sequence[int]] = None, seed: int = 0, density_gain: float = 1.0,
-                      prefix: str = "model.") -> Dict[str, torch.Tensor]:
+                      prefix: str = "model.", app_gain: float = 1.0) -> Dict[str, torch.Tensor]:
     """Reference-style random initialisation of every parameter, deterministic in ``seed`` (CPU generator),
     keyed like ``RenderLightfield.state_dict()`` (``model.embedding_model...``, ``model.color_model.net...``)."""
     grid = list(grid) if grid is not None else default_grid(sig)
@@ -153,4 +159,6 @@ def seeded_state_dict(sig: Signature, grid: Optional[Sequence[int]] = None, seed
         sd[f"{prefix}color_model.{k}"] = v.detach().clone()
     if density_gain != 1.0:
         sd = scale_density(sd, density_gain)
+    if app_gain != 1.0:
+        sd = scale_appearance(sd, app_gain)
     return sd

@@ -19,7 +19,7 @@ from .rendering import render_chunked, render_fn_dict
 
 
 class INRSystem(nn.Module):
-    def __init__(self, cfg, dm=None, dataset: Optional[dict] = None, mlp_mode: str = "fp32"):
+    def __init__(self, cfg, dm=None, dataset: Optional[dict] = None, mlp_mode: str = "auto"):
         super().__init__()
         self.cfg = to_cfg(cfg)
         self.dm = dm

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HR_ABI_VERSION 6
+#define HR_ABI_VERSION 7
 
 #define HR_MAX_GROUPS 4   /* ray-parameterisation groups feeding the sample net (ray.py:235-263) */
 #define HR_MAX_LAYERS 10  /* Linear layers of the sample net (mlp.py:127-154) */
@@ -195,10 +195,51 @@ int hr_render(hr_handle* h, const float* rays, int64_t n_rays, float* rgb,
 /* Debug/bisect variant (SURVEY.md section 4 "stage-boundary tests").  Any output pointer may be
  * NULL.  mlp_out [n, mlp_out] is in the reference's order (sample-major, ray.py:333);
  * distances [n,S] sorted t (base.py:206-210,257); points [n,S,3] final sample points (after flow
- * and offset); sigma [n,S]; weights [n,S] compositing weights (tensorf_utils.py:242-253). */
+ * and offset); sigma [n,S]; weights [n,S] compositing weights (tensorf_utils.py:242-253); rgb_samples [n,S,3] the shaded
+ * colour of every sample (renderModule output scattered by app_mask, tensorf_dynamic.py:757-777) before the colour transform. */
 int hr_render_stages(hr_handle* h, const float* rays, int64_t n_rays, float* rgb,
-                     float* mlp_out, float* distances, float* points, float* sigma, float* weights,
+                     float* mlp_out, float* distances, float* points, float* sigma, float* weights, float* rgb_samples,
                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- extra outputs of the colour net ----
+ * Replaces: the `fields` / `no_over_fields` / `pred_weights_fields` render_kwargs of TensorVMKeyframeTime.forward /
+ * TensorVMNoSample.forward (nlf/nets/tensorf_dynamic.py:808-837, nlf/nets/tensorf_no_sample.py:254-278) and the per-sample
+ * dict RayPointEmbedding.forward returns to render_fn.embed (nlf/embedding/embedding.py:100-117).  A field is a key of the
+ * dict `x` that reaches the colour net after `extract_fields`; the render kernel's epilogue reduces it in the warp that owns
+ * the ray, nothing per-sample is written unless HR_FIELD_NO_OVER asks for it. */
+enum {
+  HR_FIELD_POINTS = 0,      /* x['points']       3 channels (after flow and offset)                   */
+  HR_FIELD_DISTANCES = 1,   /* x['distances']    1           (sorted, contracted)                      */
+  HR_FIELD_BASE_TIMES = 2,  /* x['base_times']   1           keyframe time (flow_utils.py:18-31)       */
+  HR_FIELD_TIME_OFFSET = 3, /* x['time_offset']  1           t - base_time                             */
+  HR_FIELD_TIMES = 4,       /* x['times']        1           rays[:, -1] broadcast (point.py:864-867)  */
+  HR_FIELD_VIEWDIRS = 5,    /* x['viewdirs']     3           rays[:, 3:6] broadcast                    */
+  HR_FIELD_WEIGHTS = 6,     /* x['weights']      1           ones (base.py:183-191, no weight_fn)      */
+  /* per-sample heads of the sample net after their activation (ray.py:333-337), reachable through render_kwargs['fields']
+   * (ExtractFieldsEmbedding adds them, point.py:236-244) */
+  HR_FIELD_COLOR_SCALE = 7,   /* x['color_scale']   3                                                    */
+  HR_FIELD_COLOR_SHIFT = 8,   /* x['color_shift']   3                                                    */
+  HR_FIELD_SPATIAL_FLOW = 9,  /* x['spatial_flow']  3   as AdvectPoints leaves it (point.py:815-817)           */
+  HR_FIELD_SIGMA = 10,        /* x['sigma']         1                                                    */
+  HR_FIELD_POINT_SIGMA = 11,  /* x['point_sigma']   1                                                    */
+  HR_FIELD_POINT_OFFSET = 12, /* x['point_offset']  3   as PointOffset leaves it: act(.) * (1 - sigma) (point.py:383-389) */
+  HR_N_FIELDS = 13
+};
+enum {
+  HR_FIELD_OVER = 0,         /* out [n, dim]   = sum_s w_s * x_s            (tensorf_dynamic.py:832-836)            */
+  HR_FIELD_NO_OVER = 1,      /* out [n, S*dim] = x                          (:824-825)                              */
+  HR_FIELD_PRED_WEIGHTS = 2  /* out [n, dim]   = sum_s alpha2weights(x['weights'])_s * x_s   (:818-819, :826-830)   */
+};
+typedef struct hr_field_request {
+  int32_t field;  /* HR_FIELD_*                       */
+  int32_t mode;   /* HR_FIELD_OVER / NO_OVER / PRED_WEIGHTS */
+  float* out;     /* device buffer, shape per mode    */
+} hr_field_request;
+
+/* hr_render plus extra outputs: rgb [n,3]; render_weights [n,S] (the 'render_weights' key, :822-823) when non-NULL; every
+ * request in req[0..n_req).  A field the pipeline does not carry (e.g. base_times of a static model) is an error. */
+int hr_render_fields(hr_handle* h, const float* rays, int64_t n_rays, float* rgb, float* render_weights,
+                     const hr_field_request* req, int32_t n_req, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Replaces: INRSystem.forward(coords) on HOST buffers, i.e. the `.cuda()` upload, render_chunked
  * (nlf/rendering.py:100-150) and the `.cpu()` read-back of validation_video

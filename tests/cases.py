@@ -38,6 +38,15 @@ CASES: Dict[str, dict] = {
     "technicolor_z_scale": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, variant="z_scale"), n=128, seed=16, gain=30.0),
     "immersive_sphere_new": dict(builtin="neural_3d_z_plane", over=dict(n_voxels=32 ** 3, z_channels=32, variant=["sphere_new", "outward_facing"]), n=160, seed=17, gain=30.0),
     "donerf_sphere_new": dict(builtin="donerf_sphere", over=dict(n_voxels=32 ** 3, variant="sphere_new"), n=192, seed=18, gain=30.0),
+    # sample-net shapes beyond the headline one: encoded input wider than 32 features (two input chunks on the tensor-core
+    # path), with and without the time group
+    "donerf_wide_pe": dict(builtin="donerf_sphere", over=dict(n_voxels=32 ** 3, variant="wide_pe"), n=192, seed=19, gain=30.0),
+    "neural3d_wide_pe": dict(builtin="neural_3d_z_plane", over=dict(n_voxels=32 ** 3, z_channels=32, variant="wide_pe"), n=160, seed=20, gain=30.0),
+    # appearance-sensitive family: density high enough that sum(w) -> 1 and appearance tables at O(1) feature scale, so that
+    # an error in the appearance gather shows in RGB far above the 1e-4 gate (tests/test_parity_bites.py quantifies it)
+    "technicolor_app": dict(builtin="technicolor_z_plane", over=dict(n_voxels=48 ** 3), n=256, seed=21, gain=600.0, app_gain=6.0),
+    "neural3d_app": dict(builtin="neural_3d_z_plane", over=dict(n_voxels=40 ** 3), n=160, seed=22, gain=100.0, app_gain=6.0),
+    "donerf_app": dict(builtin="donerf_sphere", over=dict(n_voxels=40 ** 3), n=256, seed=23, gain=100.0, app_gain=10.0),
     "immersive_sphere_like": dict(builtin="neural_3d_z_plane", over=dict(n_voxels=32 ** 3, z_channels=32, variant=["sphere", "outward_facing"]), n=160, seed=14, gain=30.0),
 }
 
@@ -54,6 +63,12 @@ class Case:
     n_samples: int
 
 
+# render_kwargs of the extra-field fixtures (tensorf_dynamic.py:808-837): composited, raw per-sample and pred-weighted
+# outputs, including a head that only reaches the colour net because it is named here (point.py:236-244)
+FIELD_KWARGS = {"fields": ["render_weights", "distances", "points", "sigma", "viewdirs", "point_offset"],
+                "no_over_fields": ["sigma"], "pred_weights_fields": ["viewdirs"]}
+
+
 def state_hash(sd: Dict[str, torch.Tensor]) -> str:
     h = hashlib.sha256()
     for k in sorted(sd.keys()):
@@ -66,7 +81,7 @@ def build_case(name: str, n: int = None) -> Case:
     spec = CASES[name]
     cfg, ds = configs.get(spec["builtin"], **spec["over"])
     sig = lower(cfg, ds)
-    sd = seeded_state_dict(sig, seed=spec["seed"], density_gain=spec["gain"])
+    sd = seeded_state_dict(sig, seed=spec["seed"], density_gain=spec["gain"], app_gain=spec.get("app_gain", 1.0))
     r = rays_mod.for_signature(sig, n or spec["n"], seed=100 + spec["seed"])
     return Case(name=name, model_cfg=cfg, model_cfg_plain=to_plain(cfg), dataset=ds, sig=sig, rays=r, state_dict=sd,
                 n_samples=sig.n_samples)

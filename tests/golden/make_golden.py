@@ -5,9 +5,11 @@ Only runnable where /root/reference exists (the build container).  The fixtures 
 the reference does not.  Each fixture stores: the case description, the rays, a SHA-256 of the seeded
 parameters (parameters are regenerated from the seed by ``tests/cases.py`` -- torch's CPU generators are
 deterministic -- and the hash guards against drift), and the reference outputs:
-``rgb``, ``points``/``distances`` from ``render_fn.embed`` (nlf/rendering.py:79-84), ``render_weights``
-(nlf/nets/tensorf_dynamic.py:821-823) and the sample-net output of the first 64 rays (forward hook on
-``BaseMLP``).
+``rgb``, ``points``/``distances`` from ``render_fn.embed`` (nlf/rendering.py:79-84) and every other key that call returns
+(``embed__<key>``), ``render_weights`` (nlf/nets/tensorf_dynamic.py:821-823), the sample-net output of the first 64 rays
+(forward hook on ``BaseMLP``), the per-sample shaded colour ``rgb_samples`` (the colour net's ``renderModule`` wrapped, its
+output scattered by ``app_mask`` like tensorf_dynamic.py:757-777) and the extra outputs the colour net returns for
+``tests.cases.FIELD_KWARGS`` (``field__<key>``).
 
     python tests/golden/make_golden.py [case ...]
 """
@@ -23,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import ref_shim  # noqa: E402
-from tests.cases import CASES, build_case, state_hash  # noqa: E402
+from tests.cases import CASES, FIELD_KWARGS, build_case, state_hash  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -44,12 +46,30 @@ def main():
         hook = ref.model.embedding_model.embeddings[0].net.register_forward_hook(
             lambda mod, inp, out: captured.__setitem__("mlp_out", out.detach().clone()))
         from nlf.rendering import render_chunked
+        # the colour net's shading function, wrapped: renderModule(points, viewdirs, app_features, kwargs) -> [M', 3]
+        net = ref.model.color_model.net
+        inner = net.renderModule
+
+        def spy(*a, **k):
+            r = inner(*a, **k)
+            captured["valid_rgbs"] = r.detach().clone()
+            return r
+
+        net.renderModule = spy
         with torch.no_grad():
-            out = render_chunked(case.rays.clone(), ref, {"fields": ["render_weights"]}, case.rays.shape[0])
+            out = render_chunked(case.rays.clone(), ref, dict(FIELD_KWARGS), case.rays.shape[0])
             emb = ref.embed(case.rays.clone())
+        net.renderModule = inner
         hook.remove()
         S = case.n_samples
         n = case.rays.shape[0]
+        w = out["render_weights"].reshape(n, S)
+        app_mask = w > float(net.rayMarch_weight_thres)
+        rgb_samples = torch.zeros(n, S, 3)
+        if app_mask.any():
+            rgb_samples[app_mask] = captured["valid_rgbs"]
+        extra = {f"field__{k}": v.reshape(n, -1).numpy() for k, v in out.items() if k not in ("rgb", "render_weights")}
+        extra.update({f"embed__{k}": v.reshape(n, -1).numpy() for k, v in emb.items() if k not in ("points", "distances")})
         np.savez_compressed(
             os.path.join(OUT, f"{name}.npz"),
             rays=case.rays.numpy(),
@@ -58,7 +78,9 @@ def main():
             points=emb["points"].reshape(n, S, 3).numpy(),
             distances=emb["distances"].reshape(n, S).numpy(),
             mlp_out=captured["mlp_out"][:64].numpy(),
+            rgb_samples=rgb_samples.numpy(),
             state_sha256=np.array(state_hash(case.state_dict)),
+            **extra,
         )
         print(f"{name}: n={n} S={S} rgb mean {float(out['rgb'].mean()):.4f} std {float(out['rgb'].std()):.4f} "
               f"sum(w) mean {float(out['render_weights'].reshape(n, S).sum(-1).mean()):.3f}")

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle.hyperreel_oracle import HyperReelOracle
-from tests.cases import CASES, build_case, state_hash
+from tests.cases import CASES, FIELD_KWARGS, build_case, state_hash
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -38,6 +38,28 @@ def test_oracle_matches_reference_golden(name, gather):
     assert np.abs(st["distances"].numpy() - g["distances"]).max() <= 2e-6
     assert np.abs(st["points"].numpy() - g["points"]).max() <= 2e-6
     assert np.abs(st["weights"].numpy() - g["render_weights"]).max() <= 2e-6
+    # the shaded colour of every sample (appearance gather + basis + SH / RGB shading), before the colour transform
+    assert np.abs(st["rgb_samples"].numpy() - g["rgb_samples"]).max() <= 5e-6
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_extra_fields_and_embed_dict_match_reference_golden(name):
+    """render_kwargs fields / no_over_fields / pred_weights_fields (tensorf_dynamic.py:808-837) and the dict render_fn.embed
+    returns (embedding.py:100-117), key set included."""
+    case = build_case(name)
+    g = load_golden(name)
+    orc = HyperReelOracle(case.model_cfg_plain, case.dataset, case.state_dict)
+    out = orc.render_fields(case.rays.clone(), dict(FIELD_KWARGS))
+    want = {k[len("field__"):] for k in g.files if k.startswith("field__")}
+    assert want == set(out) - {"rgb", "render_weights"}
+    for k in want:
+        ref = g["field__" + k]
+        assert np.abs(out[k].numpy() - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), k
+    emb = orc.embed_fields(case.rays.clone())
+    want = {k[len("embed__"):] for k in g.files if k.startswith("embed__")} | {"points", "distances"}
+    assert want == set(emb)
+    for k in want - {"points", "distances"}:
+        assert np.abs(emb[k].numpy() - g["embed__" + k]).max() <= 2e-6, k
 
 
 @pytest.mark.parametrize("name", ["technicolor_trained", "donerf_trained"])
@@ -47,3 +69,24 @@ def test_fp64_oracle_bounds_reference_rounding(name):
     g = load_golden(name)
     rgb64 = HyperReelOracle(case.model_cfg_plain, case.dataset, case.state_dict, dtype=torch.float64).render(case.rays.clone())
     assert np.abs(rgb64.float().numpy() - g["rgb"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["technicolor_app", "neural3d_app", "donerf_app"])
+def test_appearance_sensitive_fixtures_bite(name):
+    """The appearance-sensitive fixtures must make appearance errors visible: a checker fed with a 1 % error on one
+    appearance plane, or with the appearance second factor zeroed, has to miss the reference's rgb by far more than the
+    1e-4 gate (round-1 review: with sum(w) ~ 0.18 and 0.1-scale tables a 10 % plane error stayed below the gate)."""
+    case = build_case(name)
+    g = load_golden(name)
+    assert float(g["render_weights"].sum(-1).mean()) > 0.95  # transmittance saturates: every ray shows its colour
+    assert float(np.abs(g["rgb_samples"]).max()) > 0.5 and float(g["rgb"].std()) > 0.02
+
+    def err(sd):
+        rgb = HyperReelOracle(case.model_cfg_plain, case.dataset, sd).render(case.rays.clone())
+        return float(np.abs(rgb.numpy() - g["rgb"]).max())
+
+    assert err(case.state_dict) <= 2e-6
+    plane = {k: (v * 1.01 if k.endswith(("app_plane_space.0", "app_plane.0")) else v) for k, v in case.state_dict.items()}
+    assert err(plane) > 3e-4
+    second = {k: (torch.zeros_like(v) if (".app_line" in k or ".app_plane_time" in k) else v) for k, v in case.state_dict.items()}
+    assert err(second) > 0.05
