@@ -17,7 +17,7 @@
 
 namespace hr {
 cudaError_t launch_render(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
-                          const float* heads, float* rgb, long long n, const ExtraOut* so, int num_sms,
+                          const float* heads, const RgbDst& rgb, long long n, const ExtraOut* so, int num_sms,
                           cudaStream_t stream, unsigned char* rgb8);
 cudaError_t launch_generate_rays(const hr_camera& cam, int c_in, long long first, long long n, float* out, cudaStream_t st);
 }  // namespace hr
@@ -451,12 +451,21 @@ static int launch_sample_net(hr_handle* h, const float* rays, int64_t n, float* 
   return 0;
 }
 
+static hr::RgbDst one_dst(float* rgb) {
+  hr::RgbDst d{};
+  d.p[0] = rgb;
+  d.n = 1;
+  d.row0 = 0;
+  return d;
+}
+
 static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, float* mlp_out, const hr::ExtraOut* so,
-                       void* workspace, int64_t ws_bytes, cudaStream_t st, unsigned char* rgb8 = nullptr) {
+                       void* workspace, int64_t ws_bytes, cudaStream_t st, unsigned char* rgb8 = nullptr,
+                       const hr::RgbDst* scatter = nullptr) {
   if (!h) return fail("hr_render: null handle");
   if (!h->uploaded) return fail("hr_render: parameters not uploaded (call hr_upload)");
   if (n == 0) return 0;
-  if (!rays || (!rgb && !rgb8) || !workspace) return fail("hr_render: null buffer");
+  if (!rays || (!rgb && !rgb8 && !scatter) || !workspace) return fail("hr_render: null buffer");
   if (ws_bytes < hr_workspace_bytes(h, n)) return fail("hr_render: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)hr_workspace_bytes(h, n));
   if (((uintptr_t)workspace & 15) != 0) return fail("hr_render: workspace must be 16-byte aligned");
   float* heads = (float*)workspace;
@@ -471,7 +480,7 @@ static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, f
   int rc0 = launch_sample_net(h, rays, n, heads, st);
   if (rc0) return rc0;
   if (timing) { CK(cudaEventRecord(em.b, st)); CK(cudaEventRecord(er.a, st)); }
-  e = hr::launch_render(c, h->dv, h->tabs, rays, heads, rgb, n, so, h->num_sms, st, rgb8);
+  e = hr::launch_render(c, h->dv, h->tabs, rays, heads, scatter ? *scatter : one_dst(rgb), n, so, h->num_sms, st, rgb8);
   if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
   if (timing) {
     CK(cudaEventRecord(er.b, st));
@@ -492,6 +501,22 @@ int hr_render(hr_handle* h, const float* rays, int64_t n_rays, float* rgb, void*
               void* stream) {
   DeviceGuard guard(h ? h->device : 0);
   return render_impl(h, rays, n_rays, rgb, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int hr_render_scatter(hr_handle* h, const float* rays, int64_t n_rays, float* const* dst, int32_t n_dst, int64_t row0,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h) return fail("hr_render_scatter: null handle");
+  if (!dst || n_dst < 1 || n_dst > HR_MAX_PEERS) return fail("hr_render_scatter: 1..%d destination buffers", HR_MAX_PEERS);
+  if (row0 < 0) return fail("hr_render_scatter: negative row offset");
+  DeviceGuard guard(h->device);
+  hr::RgbDst d{};
+  for (int i = 0; i < n_dst; ++i) {
+    if (!dst[i]) return fail("hr_render_scatter: null destination %d", i);
+    d.p[i] = dst[i];
+  }
+  d.n = n_dst;
+  d.row0 = row0;
+  return render_impl(h, rays, n_rays, nullptr, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, &d);
 }
 
 int hr_render_stages(hr_handle* h, const float* rays, int64_t n_rays, float* rgb, float* mlp_out, float* distances,
@@ -521,7 +546,7 @@ int hr_render_fields(hr_handle* h, const float* rays, int64_t n_rays, float* rgb
     if ((f == HR_FIELD_BASE_TIMES || f == HR_FIELD_TIME_OFFSET) && !(c.dynamic || c.use_flow))
       return fail("hr_render_fields: this pipeline has no keyframe times");
     const int head_off[HR_N_FIELDS] = {0, 0, 0, 0, 0, 0, 0, c.off_cscale, c.off_cshift, c.off_flow, c.off_sigma,
-                                       c.off_point_sigma, c.off_offset};
+                                       c.off_point_sigma, c.off_offset, c.off_cscale_global, c.off_cshift_global};
     if (f >= HR_FIELD_COLOR_SCALE && head_off[f] < 0) return fail("hr_render_fields: the sample net has no head for field %d", f);
     so.field_out[f] = req[i].out;
     so.field_mode[f] = m;
@@ -678,7 +703,7 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
     int j = 0;
     for (int64_t off = 0; off < n_rays; off += per, ++j) {
       const int64_t m = (n_rays - off < per) ? (n_rays - off) : per;
-      cudaError_t e = hr::launch_render(c, h->dv, h->tabs, d_rays + off * c.c_in, heads + off * (int64_t)c.mlp_out, d_rgb + off * 3, m,
+      cudaError_t e = hr::launch_render(c, h->dv, h->tabs, d_rays + off * c.c_in, heads + off * (int64_t)c.mlp_out, one_dst(d_rgb + off * 3), m,
                                         nullptr, h->num_sms, s0, nullptr);
       if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
       h->launches += 1;
@@ -705,7 +730,7 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
     int j = 0;
     for (int64_t off = 0; off < n_rays; off += per, ++j) {
       const int64_t m = (n_rays - off < per) ? (n_rays - off) : per;
-      e = hr::launch_render(c, h->dv, h->tabs, d_rays + off * c.c_in, heads + off * (int64_t)c.mlp_out, d_rgb + off * 3, m, nullptr,
+      e = hr::launch_render(c, h->dv, h->tabs, d_rays + off * c.c_in, heads + off * (int64_t)c.mlp_out, one_dst(d_rgb + off * 3), m, nullptr,
                             h->num_sms, s0, nullptr);
       if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
       h->launches += 1;

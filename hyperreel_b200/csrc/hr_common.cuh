@@ -41,6 +41,15 @@ struct Derived {
   int kt;               // rows of the (axis, time) planes = number of keyframes
 };
 
+// Where the finished pixels go: one or more [n_total,3] fp32 buffers (the local output; or, for ray-sharded rendering, the
+// same row range of every rank's gather buffer, peer pointers mapped over NVLink -- the render kernel's epilogue is the
+// gather).  `row0` is added to the ray index.
+struct RgbDst {
+  float* p[HR_MAX_PEERS];
+  int n;
+  long long row0;
+};
+
 // Outputs beyond rgb, produced by the EXTRA variant of the render kernel (all pointers may be null):
 //   * per-sample dumps for stage-boundary parity tests (hr_render_stages);
 //   * the extra composited fields of the reference's colour nets (tensorf_dynamic.py:808-837, tensorf_no_sample.py:254-278):

@@ -12,98 +12,12 @@
 //     nlf/nets/tensorf_no_sample.py:47-126).
 // Nothing per-sample ever goes to HBM: rays (4*c_in B) + sample-net heads in, rgb (12 B) out.
 #include "hr_common.cuh"
+#include "hr_geom.cuh"
 
 namespace hr {
 
 static constexpr int kWarpsPerCta = 8;
 static constexpr int kMinCtasPerSm = 3;
-static constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-// Ascending bitonic sort of 32*SPL keys, element e = reg*32 + lane (reference: torch.argsort +
-// gather of the distances only, utils/intersect_utils.py:12-16; ties are equal values).
-template <int SPL>
-__device__ __forceinline__ void sort_keys(float (&k)[SPL], int lane) {
-  constexpr int NE = 32 * SPL;
-#pragma unroll
-  for (int size = 2; size <= NE; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride >= 32) {
-        // partner lives in the other register of the same lane (SPL == 2, stride == 32, size == 64)
-        float lo = fminf(k[0], k[SPL - 1]), hi = fmaxf(k[0], k[SPL - 1]);
-        k[0] = lo;
-        k[SPL - 1] = hi;
-      } else {
-#pragma unroll
-        for (int r = 0; r < SPL; ++r) {
-          int e = r * 32 + lane;
-          float other = __shfl_xor_sync(kFull, k[r], stride);
-          bool up = ((e & size) == 0);
-          bool lower = ((lane & stride) == 0);
-          k[r] = (lower == up) ? fminf(k[r], other) : fmaxf(k[r], other);
-        }
-      }
-    }
-  }
-}
-
-// mipnerf inverse contraction of a scalar distance (reference: nlf/contract.py:143-158).
-__device__ __forceinline__ float inv_contract_distance(const hr_config& cfg, const Derived& dv, float d) {
-  d = __fmul_rn(__fmul_rn(d, 0.5f), 2.0f);  // distance_activation = identity: (d/2)*2
-  d = fminf(fmaxf(d, -2.0f), 2.0f);
-  float t = __fsub_rn(2.0f, fabsf(d));
-  float inv = __fadd_rn(__fdiv_rn(t, dv.dist_scale_fac), dv.inv_end_dist);
-  float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
-  float far_v = __fmul_rn(sgn, __fdiv_rn(1.0f, inv));
-  float v = (fabsf(d) < 1.0f) ? d : far_v;
-  return __fmul_rn(v, cfg.contract_start_distance);
-}
-
-// mipnerf point contraction (reference: nlf/contract.py:178-192).
-__device__ __forceinline__ void contract_point(const hr_config& cfg, const Derived& dv, float& x, float& y, float& z) {
-  x = __fdiv_rn(x, cfg.contract_start_radius);
-  y = __fdiv_rn(y, cfg.contract_start_radius);
-  z = __fdiv_rn(z, cfg.contract_start_radius);
-  float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
-  float inv = __fdiv_rn(1.0f, fabsf(dist));
-  float t = __fmul_rn(__fsub_rn(inv, dv.inv_end_rad), dv.rad_scale_fac);
-  if (!(dist < 1.0f)) {
-    float s = __fsub_rn(2.0f, t);
-    x = __fmul_rn(__fdiv_rn(x, dist), s);
-    y = __fmul_rn(__fdiv_rn(y, dist), s);
-    z = __fmul_rn(__fdiv_rn(z, dist), s);
-  }
-}
-
-// bbox / z_depth contraction of a point: (p - min) / den per axis (reference: nlf/contract.py:83-84, :109-110).
-__device__ __forceinline__ void contract_point_affine(const hr_config& cfg, float& x, float& y, float& z) {
-  x = __fdiv_rn(__fsub_rn(x, cfg.contract_affine_min[0]), cfg.contract_affine_den[0]);
-  y = __fdiv_rn(__fsub_rn(y, cfg.contract_affine_min[1]), cfg.contract_affine_den[1]);
-  z = __fdiv_rn(__fsub_rn(z, cfg.contract_affine_min[2]), cfg.contract_affine_den[2]);
-}
-// inverse contraction of a sample position (base.py:132-133): mipnerf (:143-158) or distance * fac (:77-78, :103-104)
-__device__ __forceinline__ float inv_contract_sample(const hr_config& cfg, const Derived& dv, float d) {
-  return (cfg.contract_type == HR_CONTRACT_AFFINE) ? __fmul_rn(d, cfg.contract_dist_fac) : inv_contract_distance(cfg, dv, d);
-}
-
-// Real SH basis, degree 2 (reference: utils/sh_utils.py:94-119).
-__device__ __forceinline__ void sh_basis9(float x, float y, float z, float (&Y)[9]) {
-  const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
-  const float C20 = 1.0925484305920792f, C21 = -1.0925484305920792f, C22 = 0.31539156525252005f,
-              C23 = -1.0925484305920792f, C24 = 0.5462742152960396f;
-  float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  Y[0] = C0;
-  Y[1] = -C1 * y;
-  Y[2] = C1 * z;
-  Y[3] = -C1 * x;
-  Y[4] = C20 * xy;
-  Y[5] = C21 * yz;
-  Y[6] = C22 * (2.0f * zz - xx - yy);
-  Y[7] = C23 * xz;
-  Y[8] = C24 * (xx - yy);
-}
 
 // One factor table fetch for one sample, spread over the 4 lanes of a quad.
 //   C == 8 : lane (xt, alt) reads the 16-byte half `alt` of texel x0+xt in rows y0 (a) and y0+1 (b)
@@ -195,7 +109,7 @@ template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool EXTRA>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (C1 + C2 == 0 || SPL == 1) ? 3 : 2)
 render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Derived dv,
               const __grid_constant__ RenderTabs tabs, const float* __restrict__ rays,
-              const float* __restrict__ heads, float* __restrict__ rgb_out, long long n_rays, ExtraOut so,
+              const float* __restrict__ heads, const __grid_constant__ RgbDst dst, long long n_rays, ExtraOut so,
               unsigned char* __restrict__ rgb8_out) {
   constexpr int NT = C0 + C1 + C2;
   constexpr int ROWS = (SHADE == HR_SHADE_SH) ? 9 : 1;
@@ -677,6 +591,8 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
             case HR_FIELD_POINT_OFFSET: dim = 3; hoff = cfg.off_offset; hact = &cfg.act_offset; break;
             case HR_FIELD_COLOR_SCALE: dim = 3; hoff = cfg.off_cscale; hact = &cfg.act_cscale; break;
             case HR_FIELD_COLOR_SHIFT: dim = 3; hoff = cfg.off_cshift; hact = &cfg.act_cshift; break;
+            case HR_FIELD_COLOR_SCALE_GLOBAL: dim = 3; hoff = cfg.off_cscale_global; hact = &cfg.act_cscale_global; break;
+            case HR_FIELD_COLOR_SHIFT_GLOBAL: dim = 3; hoff = cfg.off_cshift_global; hact = &cfg.act_cshift_global; break;
             default: break;
           }
           for (int c = 0; c < dim; ++c) {
@@ -745,8 +661,9 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       accB[1] += __shfl_xor_sync(kFull, accB[1], d);
       accB[2] += __shfl_xor_sync(kFull, accB[2], d);
     }
+    float v = 0.0f;
     if (lane < 3) {
-      float v = accq + ((lane == 0) ? accB[0] : ((lane == 1) ? accB[1] : accB[2]));
+      v = accq + ((lane == 0) ? accB[0] : ((lane == 1) ? accB[1] : accB[2]));
       if (cfg.white_bg && !cfg.black_bg) v = v + (1.0f - accw);
       if (cfg.off_cscale_global >= 0) {
         // scale_shift_color_one (utils/tensorf_utils.py:275-281): the heads of sample 0 (MLP order) act on the pixel
@@ -758,16 +675,21 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       if (rgb8_out != nullptr) {
         // to8b (utils/__init__.py:47): (255 * clip(x, 0, 1)).astype(uint8) -- truncation
         rgb8_out[ray * 3 + lane] = (unsigned char)(int)__fmul_rn(255.0f, fminf(fmaxf(v, 0.0f), 1.0f));
-      } else {
-        rgb_out[ray * 3 + lane] = v;
       }
+    }
+    if (rgb8_out == nullptr) {
+      // lane l stores channel l % 3 into destination l / 3: one store instruction covers every destination buffer
+      // (the local output, or all ranks' gather buffers when the frame is ray-sharded)
+      const float vv = __shfl_sync(kFull, v, lane % 3);
+      const int d = lane / 3;
+      if (d < dst.n) dst.p[d][(dst.row0 + ray) * 3 + (lane % 3)] = vv;
     }
   }
 }
 
 template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE>
 static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
-                              const float* heads, float* rgb, long long n, const ExtraOut* so, int num_sms,
+                              const float* heads, const RgbDst& rgb, long long n, const ExtraOut* so, int num_sms,
                               cudaStream_t stream, unsigned char* rgb8) {
   constexpr int ROWS = (SHADE == HR_SHADE_SH) ? 9 : 1;
   constexpr int NT = C0 + C1 + C2;
@@ -787,7 +709,7 @@ static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const Ren
 
 template <int SPL, bool DYN, int C0, int C1, int C2>
 static cudaError_t launch_shade(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
-                                const float* heads, float* rgb, long long n, const ExtraOut* so, int num_sms,
+                                const float* heads, const RgbDst& rgb, long long n, const ExtraOut* so, int num_sms,
                                 cudaStream_t stream, unsigned char* rgb8) {
   if (cfg.shading == HR_SHADE_SH)
     return launch_one<SPL, DYN, C0, C1, C2, HR_SHADE_SH>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
@@ -796,7 +718,7 @@ static cudaError_t launch_shade(const hr_config& cfg, const Derived& dv, const R
 
 template <int SPL, bool DYN>
 static cudaError_t launch_comps(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
-                                const float* heads, float* rgb, long long n, const ExtraOut* so, int num_sms,
+                                const float* heads, const RgbDst& rgb, long long n, const ExtraOut* so, int num_sms,
                                 cudaStream_t stream, unsigned char* rgb8) {
   const int c0 = cfg.n_sigma[0], c1 = cfg.n_sigma[1], c2 = cfg.n_sigma[2];
   if (c0 == 8 && c1 == 0 && c2 == 0)
@@ -810,7 +732,7 @@ static cudaError_t launch_comps(const hr_config& cfg, const Derived& dv, const R
 
 // Entry used by hr_api.cu.  Returns cudaErrorInvalidValue for an unsupported component layout.
 cudaError_t launch_render(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
-                          const float* heads, float* rgb, long long n, const ExtraOut* so, int num_sms,
+                          const float* heads, const RgbDst& rgb, long long n, const ExtraOut* so, int num_sms,
                           cudaStream_t stream, unsigned char* rgb8) {
   const bool two = cfg.n_samples > 32;
   if (cfg.dynamic) {

@@ -15,6 +15,7 @@ HR_ABI_VERSION = 7
 HR_MAX_GROUPS = 4
 HR_MAX_LAYERS = 10
 HR_MAX_SAMPLES = 64
+HR_MAX_PEERS = 8
 
 ACT_IDENTITY, ACT_SIGMOID, ACT_TANH = 0, 1, 2
 PARAM_IDENTITY, PARAM_TWO_PLANE, PARAM_PLUECKER = 0, 1, 2
@@ -25,7 +26,8 @@ DENSE_RELU, DENSE_SOFTPLUS, DENSE_RELU_ABS = 0, 1, 2
 MLP_FP32_SIMT, MLP_BF16X3_TC = 0, 1
 # extra fields of the colour net (hr_render_fields): key of the reference's dict `x` -> HR_FIELD_* id
 FIELDS = {"points": 0, "distances": 1, "base_times": 2, "time_offset": 3, "times": 4, "viewdirs": 5, "weights": 6,
-          "color_scale": 7, "color_shift": 8, "spatial_flow": 9, "sigma": 10, "point_sigma": 11, "point_offset": 12}
+          "color_scale": 7, "color_shift": 8, "spatial_flow": 9, "sigma": 10, "point_sigma": 11, "point_offset": 12,
+          "color_scale_global": 13, "color_shift_global": 14}
 FIELD_OVER, FIELD_NO_OVER, FIELD_PRED_WEIGHTS = 0, 1, 2
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -113,6 +115,8 @@ EXPORTS = {
     "hr_upload": (C.c_int, [C.c_void_p, C.POINTER(hr_params), C.c_void_p]),
     "hr_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
     "hr_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hr_render_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p,
+                                     C.c_int64, C.c_void_p]),
     "hr_render_stages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hr_render_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(hr_field_request),

@@ -177,7 +177,8 @@ class LightfieldModel(nn.Module):
             raise UnsupportedPipeline(f"field '{key}' is not produced by the fused path")
         if key not in self._available_fields():
             raise KeyError(key)  # the reference fails the same way on x[key]
-        dims = {"points": 3, "viewdirs": 3, "color_scale": 3, "color_shift": 3, "spatial_flow": 3, "point_offset": 3}
+        dims = {"points": 3, "viewdirs": 3, "color_scale": 3, "color_shift": 3, "spatial_flow": 3, "point_offset": 3,
+                "color_scale_global": 3, "color_shift_global": 3}
         return L.FIELDS[key], dims.get(key, 1)
 
     # ------------------------------------------------------------------ native plumbing
@@ -215,6 +216,22 @@ class LightfieldModel(nn.Module):
         self._ensure_uploaded(torch.device("cuda", self._device_index if self._device_index is not None else torch.cuda.current_device()))
         L.check(self._lib.hr_render_host(self._handle, rays_host.data_ptr(), n, rgb_host.data_ptr(), chunk))
         return rgb_host
+
+    def render_scatter(self, rays: torch.Tensor, dst_ptrs, n_dst: int, row0: int) -> None:
+        """Render ``rays`` and store the pixels at rows ``[row0, row0 + n)`` of every ``[N_total,3]`` fp32 buffer in
+        ``dst_ptrs`` (a ctypes ``c_void_p`` array: this rank's gather buffer and the peer-mapped buffers of the other ranks):
+        the gather of ray-sharded rendering, done by the render kernel's epilogue (hr_render_scatter, ray_shard.py)."""
+        if self.training:
+            raise RuntimeError("hyperreel_b200.LightfieldModel implements the eval()/render path only; call .eval()")
+        rays = self._check_rays(rays)
+        n = rays.shape[0]
+        if n == 0:
+            return
+        self._ensure_uploaded(rays.device)
+        ws = self._workspace(n, rays.device)
+        stream = torch.cuda.current_stream(rays.device).cuda_stream
+        L.check(self._lib.hr_render_scatter(self._handle, rays.data_ptr(), n, dst_ptrs, int(n_dst), int(row0), ws.data_ptr(),
+                                            ws.numel(), stream))
 
     def render_to8b(self, rays: torch.Tensor) -> torch.Tensor:
         """rays [N,C] on the device -> uint8 rgb [N,3] on the device: the composite with ``to8b``

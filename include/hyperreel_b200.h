@@ -30,6 +30,7 @@ extern "C" {
 #define HR_MAX_GROUPS 4   /* ray-parameterisation groups feeding the sample net (ray.py:235-263) */
 #define HR_MAX_LAYERS 10  /* Linear layers of the sample net (mlp.py:127-154) */
 #define HR_MAX_SAMPLES 64 /* z_channels S (per-ray sample primitives) */
+#define HR_MAX_PEERS 8    /* destination buffers of hr_render_scatter (GPUs of one NVSwitch domain) */
 
 /* Activation y = f(x*inner_fac + shift) * outer_fac  (nlf/activations.py:53-69,121-137,163-178).
  * EaseValue (activations.py:462-496) is resolved on the host at render iteration to its inner act. */
@@ -192,6 +193,15 @@ int64_t hr_workspace_bytes(const hr_handle* h, int64_t n_rays);
 int hr_render(hr_handle* h, const float* rays, int64_t n_rays, float* rgb,
               void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Ray-sharded rendering (the reference renders a frame on rank 0 only, nlf/__init__.py:810-811).
+ * Like hr_render, but the finished pixels of rays [0, n_rays) are stored at rows [row0, row0 + n_rays) of EVERY buffer
+ * dst[0..n_dst): the caller passes its own [N_total,3] gather buffer and the peer-mapped gather buffers of the other ranks
+ * (CUDA IPC / symmetric memory over NVLink), so the render kernel's epilogue is the gather of the pixel tiles -- 12 bytes
+ * per ray and peer cross the fabric, no collective kernel follows.  The caller orders the peers' reads (a barrier after
+ * the kernel on `stream`). */
+int hr_render_scatter(hr_handle* h, const float* rays, int64_t n_rays, float* const* dst, int32_t n_dst, int64_t row0,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Debug/bisect variant (SURVEY.md section 4 "stage-boundary tests").  Any output pointer may be
  * NULL.  mlp_out [n, mlp_out] is in the reference's order (sample-major, ray.py:333);
  * distances [n,S] sorted t (base.py:206-210,257); points [n,S,3] final sample points (after flow
@@ -223,7 +233,9 @@ enum {
   HR_FIELD_SIGMA = 10,        /* x['sigma']         1                                                    */
   HR_FIELD_POINT_SIGMA = 11,  /* x['point_sigma']   1                                                    */
   HR_FIELD_POINT_OFFSET = 12, /* x['point_offset']  3   as PointOffset leaves it: act(.) * (1 - sigma) (point.py:383-389) */
-  HR_N_FIELDS = 13
+  HR_FIELD_COLOR_SCALE_GLOBAL = 13, /* x['color_scale_global'] 3  (per-sample head; the colour net uses sample 0's, tensorf_utils.py:275-281) */
+  HR_FIELD_COLOR_SHIFT_GLOBAL = 14, /* x['color_shift_global'] 3                                                                   */
+  HR_N_FIELDS = 15
 };
 enum {
   HR_FIELD_OVER = 0,         /* out [n, dim]   = sum_s w_s * x_s            (tensorf_dynamic.py:832-836)            */
