@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "hr_common.cuh"
+#include "hr_encode.cuh"
 #include "hr_mlp.cuh"
 #include "hyperreel_b200.h"
 
@@ -19,6 +20,10 @@ namespace hr {
 cudaError_t launch_render(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
                           const float* heads, const RgbDst& rgb, long long n, const ExtraOut* so, int num_sms,
                           cudaStream_t stream, unsigned char* rgb8);
+cudaError_t launch_render_bwd(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, float* const* g_sig_space,
+                              float* const* g_sig_second, float* const* g_app_space, float* const* g_app_second, float* g_basis,
+                              const float* rays, const float* heads, const float* d_rgb, float* d_heads, long long n, int clamp_output,
+                              int white_bg, int num_sms, cudaStream_t stream);
 cudaError_t launch_generate_rays(const hr_camera& cam, int c_in, long long first, long long n, float* out, cudaStream_t st);
 }  // namespace hr
 
@@ -142,6 +147,57 @@ __global__ void unpermute_heads(const float* __restrict__ src, float* __restrict
     int rem = (int)(i % (S * stride));
     int s = rem / stride, c = rem % stride;
     dst[i] = src[ray * (long long)S * stride + c * S + s];
+  }
+}
+
+__global__ void permute_heads(const float* __restrict__ src, float* __restrict__ dst, long long n, int S, int stride) {
+  // src [n][s*stride+c] (reference order) -> dst [n][c*S+s] (the kernels' channel-major rows)
+  long long total = n * (long long)S * stride;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long ray = i / (S * stride);
+    int rem = (int)(i % (S * stride));
+    int c = rem / S, s = rem % S;
+    dst[i] = src[ray * (long long)S * stride + s * stride + c];
+  }
+}
+
+__global__ void encode_rays_kernel(const __grid_constant__ hr_config cfg, const float* __restrict__ rays, float* __restrict__ enc,
+                                   long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    hr::encode_ray(cfg, rays + i * cfg.c_in, enc + i * cfg.mlp_in, 1);
+}
+
+// gradient table [H][W][C] (channel-last, the kernels' layout) -> reference layout [C][H][W]
+__global__ void unpack_channel_last(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W) {
+  long long total = (long long)C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long hw = i % ((long long)H * W);
+    int c = (int)(i / ((long long)H * W));
+    dst[i] = src[hw * C + c];
+  }
+}
+
+// gradient of the pre-blended keyframe lines [K][L][C] -> gradient of the (axis, time) plane [C][K][L]: row r collects
+// (1 - ft_k) of every keyframe k whose lower row is r and ft_k of every keyframe whose upper row is r (see pack_time_lines)
+__global__ void unblend_time_lines(const float* __restrict__ src, float* __restrict__ dst, int C, int K, int L, float inv_fac,
+                                   float time_scale, float time_offset) {
+  long long total = (long long)C * K * L;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int l = (int)(i % L);
+    int r = (int)((i / L) % K);
+    int c = (int)(i / ((long long)K * L));
+    float acc = 0.0f;
+    for (int k = 0; k < K; ++k) {
+      float base_t = __fmul_rn((float)k, inv_fac);
+      float tau = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(base_t, time_scale), time_offset), 2.0f), 1.0f);
+      float iy = __fmul_rn(__fmul_rn(__fadd_rn(tau, 1.0f), 0.5f), (float)(K - 1));
+      int it = max(0, min((int)floorf(iy), K - 2));
+      float ft = iy - (float)it;
+      float g = src[((long long)k * L + l) * C + c];
+      if (it == r) acc += (1.0f - ft) * g;
+      if (it + 1 == r) acc += ft * g;
+    }
+    dst[i] = acc;
   }
 }
 
@@ -779,6 +835,144 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
   return 0;
 }
 
+// ---- backward pass ----
+static int train_supported(const hr_config& c) {
+  if (c.isect_type == HR_ISECT_SPHERE_NEW) return fail("backward: the sphere_new primitive is not supported yet");
+  if ((c.isect_type == HR_ISECT_SPHERE || c.isect_type == HR_ISECT_CYLINDER) && c.sphere_origin_scale != 0.0f)
+    return fail("backward: learned primitive origins (origin_scale_factor != 0) are not supported yet");
+  if (c.contract_type == HR_CONTRACT_AFFINE) return fail("backward: bbox / z_depth contraction is not supported yet");
+  if (c.off_cscale_global >= 0) return fail("backward: per-ray colour heads are not supported yet");
+  return 0;
+}
+
+static int ensure_grad_tables(hr_handle* h, cudaStream_t st) {
+  const hr_config& c = h->cfg;
+  size_t want[13];
+  for (int i = 0; i < 3; ++i) {
+    const hr::PlaneTab& t = h->tabs.sig[i];
+    const size_t sp = (size_t)t.C * t.H * t.W, se = (size_t)t.C * t.H2 * t.L;
+    want[i] = sp; want[3 + i] = se; want[6 + i] = sp; want[9 + i] = se;
+  }
+  want[12] = (size_t)c.app_dim * h->tabs.n_app_total;
+  float** bufs[13] = {&h->g_sig_space[0], &h->g_sig_space[1], &h->g_sig_space[2], &h->g_sig_second[0], &h->g_sig_second[1],
+                      &h->g_sig_second[2], &h->g_app_space[0], &h->g_app_space[1], &h->g_app_space[2], &h->g_app_second[0],
+                      &h->g_app_second[1], &h->g_app_second[2], &h->g_basis};
+  for (int i = 0; i < 13; ++i) {
+    if (h->g_sizes[i] == want[i] && (*bufs[i] || want[i] == 0)) continue;
+    if (*bufs[i]) cudaFree(*bufs[i]);
+    *bufs[i] = nullptr;
+    h->g_sizes[i] = 0;
+    if (want[i] == 0) continue;
+    cudaError_t e = cudaMalloc((void**)bufs[i], want[i] * sizeof(float));
+    if (e != cudaSuccess) return fail("cudaMalloc(gradient table %zu floats): %s", want[i], cudaGetErrorString(e));
+    e = cudaMemsetAsync(*bufs[i], 0, want[i] * sizeof(float), st);
+    if (e != cudaSuccess) return fail("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    h->g_sizes[i] = want[i];
+  }
+  return 0;
+}
+
+int hr_encode_rays(hr_handle* h, const float* rays, int64_t n_rays, float* enc, void* stream) {
+  if (!h || !rays || !enc) return fail("hr_encode_rays: null argument");
+  if (n_rays == 0) return 0;
+  DeviceGuard guard(h->device);
+  encode_rays_kernel<<<grid_for(n_rays), 256, 0, (cudaStream_t)stream>>>(h->cfg, rays, enc, n_rays);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("hr_encode_rays: %s", cudaGetErrorString(e));
+  h->launches += 1;
+  return 0;
+}
+
+int hr_render_heads(hr_handle* h, const float* rays, const float* heads, int64_t n, float* rgb, const hr_train_opts* opts,
+                    void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h || !rays || !heads || !rgb || !opts || !workspace) return fail("hr_render_heads: null argument");
+  if (!h->uploaded) return fail("hr_render_heads: parameters not uploaded");
+  if (n == 0) return 0;
+  if (workspace_bytes < hr_workspace_bytes(h, n)) return fail("hr_render_heads: workspace too small");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  hr_config c = h->cfg;
+  c.clamp_output = opts->clamp_output ? 1 : 0;
+  c.white_bg = opts->white_bg ? 1 : 0;
+  if (opts->white_bg) c.black_bg = 0;
+  float* hcm = (float*)workspace;
+  permute_heads<<<grid_for(n * (long long)c.mlp_out), 256, 0, st>>>(heads, hcm, n, c.n_samples, c.head_stride);
+  cudaError_t e = hr::launch_render(c, h->dv, h->tabs, rays, hcm, one_dst(rgb), n, nullptr, h->num_sms, st, nullptr);
+  if (e != cudaSuccess) return fail("hr_render_heads: %s", cudaGetErrorString(e));
+  h->launches += 2;
+  return 0;
+}
+
+int hr_render_backward(hr_handle* h, const float* rays, const float* heads, int64_t n, const float* d_rgb, float* d_heads,
+                       const hr_train_opts* opts, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h || !rays || !heads || !d_rgb || !d_heads || !opts || !workspace) return fail("hr_render_backward: null argument");
+  if (!h->uploaded) return fail("hr_render_backward: parameters not uploaded");
+  if (train_supported(h->cfg)) return 1;
+  if (n == 0) return 0;
+  if (workspace_bytes < 2 * hr_workspace_bytes(h, n)) return fail("hr_render_backward: workspace too small (2 x hr_workspace_bytes)");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const hr_config& c = h->cfg;
+  if (ensure_grad_tables(h, st)) return 1;
+  float* hcm = (float*)workspace;
+  float* gcm = (float*)((char*)workspace + hr_workspace_bytes(h, n));
+  permute_heads<<<grid_for(n * (long long)c.mlp_out), 256, 0, st>>>(heads, hcm, n, c.n_samples, c.head_stride);
+  const int white = (opts->white_bg && !(c.black_bg && !opts->white_bg)) ? 1 : 0;
+  cudaError_t e = hr::launch_render_bwd(c, h->dv, h->tabs, h->g_sig_space, h->g_sig_second, h->g_app_space, h->g_app_second, h->g_basis,
+                                        rays, hcm, d_rgb, gcm, n, opts->clamp_output ? 1 : 0, white, h->num_sms, st);
+  if (e != cudaSuccess) return fail("hr_render_backward: %s", cudaGetErrorString(e));
+  unpermute_heads<<<grid_for(n * (long long)c.mlp_out), 256, 0, st>>>(gcm, d_heads, n, c.n_samples, c.head_stride);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("hr_render_backward: %s", cudaGetErrorString(e));
+  h->launches += 3;
+  return 0;
+}
+
+int hr_grad_zero(hr_handle* h, void* stream) {
+  if (!h) return fail("hr_grad_zero: null handle");
+  if (!h->uploaded) return fail("hr_grad_zero: parameters not uploaded");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ensure_grad_tables(h, st)) return 1;
+  float* bufs[13] = {h->g_sig_space[0], h->g_sig_space[1], h->g_sig_space[2], h->g_sig_second[0], h->g_sig_second[1], h->g_sig_second[2],
+                     h->g_app_space[0], h->g_app_space[1], h->g_app_space[2], h->g_app_second[0], h->g_app_second[1], h->g_app_second[2],
+                     h->g_basis};
+  for (int i = 0; i < 13; ++i)
+    if (bufs[i]) CK(cudaMemsetAsync(bufs[i], 0, h->g_sizes[i] * sizeof(float), st));
+  return 0;
+}
+
+int hr_grad_read(hr_handle* h, const hr_grads* out, void* stream) {
+  if (!h || !out) return fail("hr_grad_read: null argument");
+  if (!h->uploaded) return fail("hr_grad_read: parameters not uploaded");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ensure_grad_tables(h, st)) return 1;
+  const hr_config& c = h->cfg;
+  for (int i = 0; i < 3; ++i) {
+    const hr::PlaneTab& t = h->tabs.sig[i];
+    if (t.C == 0) continue;
+    for (int f = 0; f < 2; ++f) {
+      float* dsp = f ? out->app_plane[i] : out->sigma_plane[i];
+      float* dse = f ? out->app_second[i] : out->sigma_second[i];
+      const float* gsp = f ? h->g_app_space[i] : h->g_sig_space[i];
+      const float* gse = f ? h->g_app_second[i] : h->g_sig_second[i];
+      if (dsp) unpack_channel_last<<<grid_for((long long)t.C * t.H * t.W), 256, 0, st>>>(gsp, dsp, t.C, t.H, t.W);
+      if (dse) {
+        if (c.dynamic)
+          unblend_time_lines<<<grid_for((long long)t.C * t.H2 * t.L), 256, 0, st>>>(gse, dse, t.C, t.H2, t.L, h->dv.time_inv_fac,
+                                                                                   h->dv.time_scale, h->dv.time_offset);
+        else
+          unpack_channel_last<<<grid_for((long long)t.C * t.H2 * t.L), 256, 0, st>>>(gse, dse, t.C, t.H2, t.L);
+      }
+    }
+  }
+  if (out->basis_mat) CK(cudaMemcpyAsync(out->basis_mat, h->g_basis, h->g_sizes[12] * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("hr_grad_read: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int64_t hr_launch_count(const hr_handle* h) { return h ? h->launches : -1; }
 
 int hr_timing_enable(hr_handle* h, int enable) {
@@ -821,6 +1015,10 @@ int hr_destroy(hr_handle* h) {
   if (!h) return 0;
   DeviceGuard guard(h->device);
   for (auto& sl : h->slots) cudaFree(sl.ptr);
+  for (int i = 0; i < 3; ++i) {
+    cudaFree(h->g_sig_space[i]); cudaFree(h->g_sig_second[i]); cudaFree(h->g_app_space[i]); cudaFree(h->g_app_second[i]);
+  }
+  cudaFree(h->g_basis);
   hr::free_mlp_tc2(h);
   drop_events(h->ev_render);
   drop_events(h->ev_mlp);

@@ -44,6 +44,13 @@ struct hr_handle {
   size_t tc_alloc_bytes = 0;  // current allocation behind tc.wpack / tc.bias (reused while the layout is unchanged)
   int tc_alloc_bias = 0;
   void* tma_encode = nullptr; // cuTensorMapEncodeTiled, from cudaGetDriverEntryPoint
+  // gradient tables of the backward pass (hr_render_backward), packed like the forward tables; allocated on first use
+  float* g_sig_space[3] = {nullptr, nullptr, nullptr};
+  float* g_sig_second[3] = {nullptr, nullptr, nullptr};
+  float* g_app_space[3] = {nullptr, nullptr, nullptr};
+  float* g_app_second[3] = {nullptr, nullptr, nullptr};
+  float* g_basis = nullptr;
+  size_t g_sizes[13] = {0};   // element counts of the 13 buffers above (to notice a resized grid)
   int64_t launches = 0;
   bool timing = false;
   std::vector<EventPair> ev_render, ev_mlp;

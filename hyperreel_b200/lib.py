@@ -11,7 +11,7 @@ import os
 import subprocess
 import threading
 
-HR_ABI_VERSION = 7
+HR_ABI_VERSION = 8
 HR_MAX_GROUPS = 4
 HR_MAX_LAYERS = 10
 HR_MAX_SAMPLES = 64
@@ -98,6 +98,15 @@ class hr_field_request(C.Structure):
     _fields_ = [("field", C.c_int32), ("mode", C.c_int32), ("out", C.c_void_p)]
 
 
+class hr_train_opts(C.Structure):
+    _fields_ = [("clamp_output", C.c_int32), ("white_bg", C.c_int32)]
+
+
+class hr_grads(C.Structure):
+    _fields_ = [("sigma_plane", C.c_void_p * 3), ("app_plane", C.c_void_p * 3), ("sigma_second", C.c_void_p * 3),
+                ("app_second", C.c_void_p * 3), ("basis_mat", C.c_void_p)]
+
+
 class hr_camera(C.Structure):
     _fields_ = [
         ("c2w", C.c_float * 12), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
@@ -125,6 +134,13 @@ EXPORTS = {
     "hr_generate_rays": (C.c_int, [C.POINTER(hr_camera), C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "hr_render_to8b": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hr_render_frame_to8b_host": (C.c_int, [C.c_void_p, C.POINTER(hr_camera), C.c_void_p, C.c_int64]),
+    "hr_encode_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "hr_render_heads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(hr_train_opts), C.c_void_p,
+                                   C.c_int64, C.c_void_p]),
+    "hr_render_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(hr_train_opts),
+                                      C.c_void_p, C.c_int64, C.c_void_p]),
+    "hr_grad_zero": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hr_grad_read": (C.c_int, [C.c_void_p, C.POINTER(hr_grads), C.c_void_p]),
     "hr_launch_count": (C.c_int64, [C.c_void_p]),
     "hr_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_timing_reset": (C.c_int, [C.c_void_p]),

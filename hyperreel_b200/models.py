@@ -52,6 +52,25 @@ def resolve_mlp_mode(name: str) -> int:
         raise ValueError(f"mlp_mode must be 'auto', 'bf16x3' or 'fp32', got {name!r}") from None
 
 
+class _RenderHeads(torch.autograd.Function):
+    """Everything after the sample net as one differentiable op: (rays, heads, VM tables, basis_mat) -> rgb.
+    forward = hr_render_heads (the fused render kernel on caller-provided heads); backward = hr_render_backward (d heads, and the
+    table / basis gradients accumulated in the handle, exported with hr_grad_read into the reference's tensor layouts)."""
+
+    @staticmethod
+    def forward(ctx, model, rays, heads, clamp_output, white_bg, *params):
+        ctx.model, ctx.opts = model, (int(clamp_output), int(white_bg))
+        ctx.save_for_backward(rays, heads)
+        ctx.param_shapes = [tuple(p.shape) for p in params]
+        return model._render_heads(rays, heads, *ctx.opts)
+
+    @staticmethod
+    def backward(ctx, d_rgb):
+        rays, heads = ctx.saved_tensors
+        d_heads, grads = ctx.model._render_backward(rays, heads, d_rgb.contiguous().float(), *ctx.opts)
+        return (None, None, d_heads, None, None) + tuple(grads)
+
+
 class LightfieldModel(nn.Module):
     def __init__(self, cfg, **kwargs):
         super().__init__()
@@ -99,7 +118,9 @@ class LightfieldModel(nn.Module):
         render_kwargs = render_kwargs or {}
         fields = list(render_kwargs.get("fields", []))
         if self.training:
-            raise RuntimeError("hyperreel_b200.LightfieldModel implements the eval()/render path only; call .eval()")
+            if fields:
+                raise UnsupportedPipeline("extra fields are produced by the eval()/render path only")
+            return {"rgb": self.render_differentiable(rays)}
         rays = self._check_rays(rays)
         n = rays.shape[0]
         rgb = torch.empty((n, 3), device=rays.device, dtype=torch.float32)
@@ -154,6 +175,95 @@ class LightfieldModel(nn.Module):
         L.check(self._lib.hr_render_fields(self._handle, rays.data_ptr(), n, rgb.data_ptr(), None, arr, len(reqs),
                                            ws.data_ptr(), ws.numel(), stream))
         return out
+
+    # ------------------------------------------------------------------ training path
+    def render_differentiable(self, rays: torch.Tensor, clamp_output: Optional[bool] = None, white_bg: Optional[bool] = None,
+                              return_heads: bool = False):
+        """rgb [N,3] with an autograd graph back to every parameter -- what ``training_step`` (nlf/__init__.py:634-709) needs.
+        Defaults follow the module mode like the reference: training -> no clamp, white background by coin flip
+        (tensorf_dynamic.py:795-806); eval -> clamp, configured background.  The sample net's Linear layers run as torch
+        ops on the library's encoded input (hr_encode_rays); everything after them is one autograd op around the fused
+        kernels (hr_render_heads / hr_render_backward)."""
+        rays = self._check_rays(rays)
+        c = self.sig.cfg
+        if clamp_output is None:
+            clamp_output = not self.training
+        if white_bg is None:
+            white_bg = bool(c.white_bg) or (self.training and not c.black_bg and bool(torch.rand(()) < 0.5))
+        white_bg = bool(white_bg) and not c.black_bg
+        self._ensure_uploaded(rays.device)
+        n = rays.shape[0]
+        enc = torch.empty((n, c.mlp_in), device=rays.device)
+        stream = torch.cuda.current_stream(rays.device).cuda_stream
+        if n:
+            L.check(self._lib.hr_encode_rays(self._handle, rays.data_ptr(), n, enc.data_ptr(), stream))
+        perm = list(self.sig.in_perm)
+        if perm != list(range(len(perm))):  # BasicPE: reference feature in_perm[k] = kernel feature k
+            inv = torch.empty(len(perm), dtype=torch.long)
+            inv[torch.tensor(perm)] = torch.arange(len(perm))
+            enc = enc.index_select(1, inv.to(rays.device))
+        net = self.embedding_model.embeddings[0].net
+        x = enc
+        last = len(net.layers) - 1
+        for i, layer in enumerate(net.layers):  # BaseMLP.forward (mlp.py:159-172)
+            lin = layer[0] if isinstance(layer, nn.Sequential) else layer
+            if i == c.mlp_skip:
+                x = torch.cat([enc, x], -1)
+            x = torch.nn.functional.linear(x, lin.weight, lin.bias)
+            if i < last:
+                x = torch.nn.functional.leaky_relu(x, c.leaky_slope)
+        tn = self.color_model.net
+        dplane, dsecond, aplane, asecond = tn.tables()
+        params = [t for t in list(dplane) + list(aplane) + list(dsecond) + list(asecond) if t.numel() > 0] + [tn.basis_mat.weight]
+        rgb = _RenderHeads.apply(self, rays, x, clamp_output, white_bg, *params)
+        return (rgb, x) if return_heads else rgb  # x: the sample-net output [N, S*stride] (gradient bisecting)
+
+    def _train_workspace(self, n, dev):
+        need = 2 * int(self._lib.hr_workspace_bytes(self._handle, n))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def _render_heads(self, rays, heads, clamp_output, white_bg):
+        n = rays.shape[0]
+        rgb = torch.empty((n, 3), device=rays.device)
+        if n == 0:
+            return rgb
+        heads = heads.detach().contiguous().float()
+        ws = self._train_workspace(n, rays.device)
+        opts = L.hr_train_opts(clamp_output, white_bg)
+        stream = torch.cuda.current_stream(rays.device).cuda_stream
+        L.check(self._lib.hr_render_heads(self._handle, rays.data_ptr(), heads.data_ptr(), n, rgb.data_ptr(), C.byref(opts),
+                                          ws.data_ptr(), ws.numel(), stream))
+        return rgb
+
+    def _render_backward(self, rays, heads, d_rgb, clamp_output, white_bg):
+        n = rays.shape[0]
+        heads = heads.detach().contiguous().float()
+        d_heads = torch.zeros_like(heads)
+        tn = self.color_model.net
+        dplane, dsecond, aplane, asecond = tn.tables()
+        stream = torch.cuda.current_stream(rays.device).cuda_stream
+        opts = L.hr_train_opts(clamp_output, white_bg)
+        L.check(self._lib.hr_grad_zero(self._handle, stream))
+        if n:
+            ws = self._train_workspace(n, rays.device)
+            L.check(self._lib.hr_render_backward(self._handle, rays.data_ptr(), heads.data_ptr(), n, d_rgb.data_ptr(), d_heads.data_ptr(),
+                                                 C.byref(opts), ws.data_ptr(), ws.numel(), stream))
+        G = L.hr_grads()
+        outs = {}
+        for name, tabs, slot in (("dp", dplane, G.sigma_plane), ("ap", aplane, G.app_plane), ("d2", dsecond, G.sigma_second),
+                                 ("a2", asecond, G.app_second)):
+            for i in range(3):
+                if tabs[i].numel() > 0:
+                    g = torch.empty(tabs[i].shape, device=rays.device, dtype=torch.float32)
+                    outs[(name, i)] = g
+                    slot[i] = g.data_ptr()
+        gb = torch.empty(tn.basis_mat.weight.shape, device=rays.device, dtype=torch.float32)
+        G.basis_mat = gb.data_ptr()
+        L.check(self._lib.hr_grad_read(self._handle, C.byref(G), stream))
+        order = [outs[(nm, i)] for nm in ("dp", "ap", "d2", "a2") for i in range(3) if (nm, i) in outs] + [gb]
+        return d_heads, order
 
     # ------------------------------------------------------------------ the dict `x` of the reference, by name
     def _extract_fields(self):

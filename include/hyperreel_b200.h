@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HR_ABI_VERSION 7
+#define HR_ABI_VERSION 8
 
 #define HR_MAX_GROUPS 4   /* ray-parameterisation groups feeding the sample net (ray.py:235-263) */
 #define HR_MAX_LAYERS 10  /* Linear layers of the sample net (mlp.py:127-154) */
@@ -292,6 +292,42 @@ int hr_render_to8b(hr_handle* h, const float* rays, int64_t n_rays, uint8_t* rgb
  * (pinned) host buffer rgb8_host [width*height, 3]; synchronous.  Replaces one iteration of validation_video /
  * NeRFGUI.test_step (nlf/__init__.py:828-891, utils/gui_utils.py:139-212). */
 int hr_render_frame_to8b_host(hr_handle* h, const hr_camera* cam, uint8_t* rgb8_host, int64_t chunk);
+
+/* ---- backward pass of the path ----
+ * Replaces: what loss.backward() runs for the render path inside INRSystem.training_step (nlf/__init__.py:634-709): the
+ * autograd graph of RayPointEmbedding + TensorVMKeyframeTime / TensorVMNoSample.  The sample net's Linear layers stay with
+ * the caller (their forward / backward are plain GEMMs on activations the caller keeps); the library provides the three
+ * pieces around them, all hand-written kernels:
+ *   hr_encode_rays      rays -> encoded sample-net input (RayParam + PE, ray.py:320-326), kernel feature order
+ *   hr_render_heads     sample-net output -> rgb, the forward of everything after the net (training or eval semantics)
+ *   hr_render_backward  d rgb -> d (sample-net output); gradients of the VM tables and basis_mat accumulate in the handle
+ *   hr_grad_zero / hr_grad_read   clear / export the accumulated parameter gradients in the reference's tensor layouts
+ * Supported: z_plane / sphere / cylinder primitives with origin_scale_factor == 0, no or mipnerf contraction, per-sample
+ * colour heads; other pipelines are rejected (hr_last_error). */
+typedef struct hr_train_opts {
+  int32_t clamp_output; /* 1: eval() forward, clamp(0,1) (tensorf_dynamic.py:805-806); 0: training forward            */
+  int32_t white_bg;     /* rgb_map += 1 - acc_map: cfg.white_bg, or the training coin flip of :795-796 drawn by the caller */
+} hr_train_opts;
+
+typedef struct hr_grads {  /* device buffers in the reference's layouts (hr_params), overwritten by hr_grad_read; NULL = skip */
+  float* sigma_plane[3];
+  float* app_plane[3];
+  float* sigma_second[3];
+  float* app_second[3];
+  float* basis_mat;
+} hr_grads;
+
+/* enc [n, mlp_in] fp32 device */
+int hr_encode_rays(hr_handle* h, const float* rays, int64_t n_rays, float* enc, void* stream);
+/* heads [n, mlp_out] in the reference's order (sample-major: column s*head_stride + c, ray.py:333); workspace as for
+ * hr_render */
+int hr_render_heads(hr_handle* h, const float* rays, const float* heads, int64_t n_rays, float* rgb, const hr_train_opts* opts,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+/* d_rgb [n,3] -> d_heads [n, mlp_out] (reference order); workspace of 2 * hr_workspace_bytes(h, n) */
+int hr_render_backward(hr_handle* h, const float* rays, const float* heads, int64_t n_rays, const float* d_rgb, float* d_heads,
+                       const hr_train_opts* opts, void* workspace, int64_t workspace_bytes, void* stream);
+int hr_grad_zero(hr_handle* h, void* stream);
+int hr_grad_read(hr_handle* h, const hr_grads* out, void* stream);
 
 /* Number of kernels hr_render launched since creation (bench.py's gpu_launches). */
 int64_t hr_launch_count(const hr_handle* h);

@@ -1,0 +1,108 @@
+"""Backward pass of the path on the GPU: gradients of every parameter against the reference's own autograd
+(tests/golden/grads_*.npz, made by tests/golden/make_golden_grads.py from the unmodified reference) and against the gradient
+oracle (training-mode forward: no clamp, white background)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hyperreel_b200 as hb
+from oracle.hyperreel_oracle import HyperReelOracle
+from tests.cases import build_case
+from tests.golden.make_golden_grads import N_RAYS, probe_indices, target_for
+from tests.test_parity_gpu import make_render
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SUPPORTED = ["technicolor_trained", "donerf_s16", "neural3d_trained"]
+
+
+def _loss(rgb, n):
+    return ((rgb - target_for(n).to(rgb.device)) ** 2).mean()
+
+
+@pytest.mark.parametrize("name", SUPPORTED)
+def test_parameter_gradients_match_reference_autograd(name):
+    g = np.load(os.path.join(GOLDEN, f"grads_{name}.npz"))
+    case = build_case(name)
+    rays = case.rays[:N_RAYS].clone().cuda()
+    render = make_render(case).cuda()
+    rgb = render.model.render_differentiable(rays, clamp_output=True)  # eval-mode forward, like the golden
+    loss = _loss(rgb, rays.shape[0])
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5
+    named = dict(render.named_parameters())
+    keys = [k[len("norm/"):] for k in g.files if k.startswith("norm/")]
+    assert len(keys) >= 17
+    for k in keys:
+        assert k in named, k
+        grad = named[k].grad
+        assert grad is not None, k
+        flat = grad.reshape(-1).cpu()
+        scale = float(g[f"max/{k}"]) + 1e-12
+        assert abs(float(flat.norm()) - float(g[f"norm/{k}"])) <= 2e-3 * float(g[f"norm/{k}"]) + 1e-9, k
+        probe = flat[probe_indices(flat.numel())].numpy()
+        assert np.abs(probe - g[f"probe/{k}"]).max() <= 1e-3 * scale + 1e-10, k
+
+
+@pytest.mark.parametrize("name", ["technicolor_app", "donerf_app", "neural3d_app"])
+@pytest.mark.parametrize("white", [False, True])
+def test_training_mode_gradients_match_the_oracle(name, white):
+    """training_step semantics (no clamp, optional white background) on the appearance-sensitive cases; every parameter
+    tensor compared entry by entry with the oracle's autograd, plus d loss / d (sample-net output)."""
+    case = build_case(name, n=200)
+    rays = case.rays.clone()
+    orc = HyperReelOracle(case.model_cfg_plain, case.dataset, case.state_dict)
+    rgb_h, leaves_h = orc.render_with_grad(rays, clamp=False, white_bg=white, heads_leaf=True)
+    _loss(rgb_h, rays.shape[0]).backward()
+    rgb_o, leaves = orc.render_with_grad(rays, clamp=False, white_bg=white)
+    _loss(rgb_o, rays.shape[0]).backward()
+    render = make_render(case).cuda()
+    render.train()
+    rgb, heads = render.model.render_differentiable(rays.cuda(), white_bg=white, return_heads=True)
+    heads.retain_grad()
+    assert float((rgb.detach().cpu() - rgb_o.detach()).abs().max()) <= 2e-5
+    _loss(rgb, rays.shape[0]).backward()
+    ref_h = leaves_h["_mlp_out"].grad
+    err_h = float((heads.grad.cpu() - ref_h).abs().max())
+    assert err_h <= 2e-3 * float(ref_h.abs().max()), f"d loss / d heads: {err_h} vs {float(ref_h.abs().max())}"
+    for k, p in render.named_parameters():
+        if k not in leaves or leaves[k].grad is None:
+            continue
+        ref = leaves[k].grad
+        scale = float(ref.abs().max()) + 1e-12
+        assert p.grad is not None, k
+        err = float((p.grad.cpu() - ref).abs().max())
+        assert err <= 2e-3 * scale, f"{k}: {err} vs scale {scale}"
+
+
+def test_unsupported_pipelines_refuse_to_train():
+    case = build_case("immersive_sphere_new", n=32)
+    render = make_render(case).cuda()
+    rgb = render.model.render_differentiable(case.rays.cuda())
+    with pytest.raises(RuntimeError):
+        rgb.sum().backward()
+
+
+def test_optimizer_step_changes_the_next_render():
+    """One Adam step on every parameter group: the library notices the new values (version counters) and re-packs."""
+    case = build_case("technicolor_app", n=512)
+    render = make_render(case).cuda()
+    render.train()
+    rays = case.rays.cuda()
+    opt = torch.optim.Adam(render.parameters(), lr=1e-2)
+    target = torch.full((rays.shape[0], 3), 0.25, device="cuda")
+    losses = []
+    for _ in range(5):
+        opt.zero_grad(set_to_none=True)
+        loss = ((render.model.render_differentiable(rays, white_bg=False) - target) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]
+    render.eval()
+    with torch.no_grad():
+        a = render(rays)["rgb"]
+    ref = HyperReelOracle(case.model_cfg_plain, case.dataset, {k: v.detach().cpu() for k, v in render.state_dict().items()}).render(case.rays.clone())
+    assert float((a.cpu() - ref).abs().max()) <= 1e-4
