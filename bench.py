@@ -311,6 +311,57 @@ def run_extra_workloads(torch, hb, dev, flush, steps, peak, peak_src):
     return out
 
 
+def run_train_step(torch, hb, dev, steps):
+    """BASELINE config 3 ("train+render"): INRSystem.training_step (forward in training mode, MSE, backward through the
+    render-backward kernel and the sample net, one Adam per optimiser group, re-pack of the updated parameters) on the
+    Technicolor shape at the final grid.  Reported per batch size: whole-step ms and the render-backward kernel alone with the
+    bytes it reduces into the gradient tables (24*C bytes per sample, field and VM group: 4 plane taps + 2 line taps)."""
+    hb_, cfg, ds, sig, sd = build_workload(gain=600.0, app_gain=6.0)
+    system = hb.INRSystem(hb.to_cfg({"model": cfg, "training": {"ray_chunk": 1 << 20, "iters_per_epoch": 4000}, "dataset": ds}))
+    system.load_state_dict(sd)
+    system.to(dev)
+    system.configure_optimizers()
+    model = system.render_fn.model
+    c = sig.cfg
+    red_bytes_per_ray = c.n_samples * sum(24 * int(x) for comps in (c.n_sigma, c.n_app) for x in comps)
+    peak, peak_src = measured_peaks()
+    out = {"what": "technicolor_z_plane, grid 1007x1007x503, K=12: INRSystem.training_step (image loss only), fp32; sample-net "
+                   "Linear layers forward/backward as torch (cuBLAS SGEMM) ops, everything else hand-written kernels",
+           "batches": []}
+    for n in (16384, 65536):
+        g = torch.Generator().manual_seed(3)
+        batch = {"coords": hb.rays.for_signature(sig, n, seed=9).to(dev), "rgb": torch.rand(n, 3, generator=g).to(dev)}
+        for _ in range(3):
+            system.training_step(batch)
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            system.training_step(batch)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        model.timing(True)
+        for _ in range(steps):
+            system.training_step(batch)
+        torch.cuda.synchronize()
+        tm = model.timing_read()
+        model.timing(False)
+        bw = tm["backward_ms"]
+        out["batches"].append({"rays": n, "train_step_ms": ms, "Mrays_per_s": n / (ms * 1e-3) / 1e6,
+                               "render_backward_kernel_ms": bw,
+                               "roofline": {"bound": "l2 atomics (reported against the HBM copy peak)", "unit": "GB/s",
+                                            "reduction_bytes_per_ray": red_bytes_per_ray,
+                                            "achieved": (red_bytes_per_ray * n / (bw * 1e-3) / 1e9) if bw > 0 else None,
+                                            "peak": peak, "frac": (red_bytes_per_ray * n / (bw * 1e-3) / 1e9 / peak) if bw > 0 else None,
+                                            "peak_source": peak_src}})
+    del system
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -441,6 +492,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_extras:
         peak, peak_src = measured_peaks()
         extras = run_extra_workloads(torch, hb, dev, flush, max(3, args.steps // 4), peak, peak_src)
+        try:
+            extras["train_step"] = run_train_step(torch, hb, dev, max(3, args.steps // 4))
+        except Exception as e:  # the render line must survive a failure of the next-tier row
+            extras["train_step"] = {"unavailable": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:  # the reference's op sequence, eager PyTorch, on this same B200 (full 65 536-ray batch)
             mr, ms, _ = time_oracle(cfg, ds, sd, sig, hb, 5, 2, n, device=f"cuda:{local}")

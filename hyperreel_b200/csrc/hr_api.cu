@@ -917,10 +917,14 @@ int hr_render_backward(hr_handle* h, const float* rays, const float* heads, int6
   float* hcm = (float*)workspace;
   float* gcm = (float*)((char*)workspace + hr_workspace_bytes(h, n));
   permute_heads<<<grid_for(n * (long long)c.mlp_out), 256, 0, st>>>(heads, hcm, n, c.n_samples, c.head_stride);
-  const int white = (opts->white_bg && !(c.black_bg && !opts->white_bg)) ? 1 : 0;
+  const int white = opts->white_bg ? 1 : 0;
+  EventPair eb{nullptr, nullptr};
+  const bool timing = h->timing && h->ev_bwd.size() < 8192;
+  if (timing) { CK(cudaEventCreate(&eb.a)); CK(cudaEventCreate(&eb.b)); CK(cudaEventRecord(eb.a, st)); }
   cudaError_t e = hr::launch_render_bwd(c, h->dv, h->tabs, h->g_sig_space, h->g_sig_second, h->g_app_space, h->g_app_second, h->g_basis,
                                         rays, hcm, d_rgb, gcm, n, opts->clamp_output ? 1 : 0, white, h->num_sms, st);
   if (e != cudaSuccess) return fail("hr_render_backward: %s", cudaGetErrorString(e));
+  if (timing) { CK(cudaEventRecord(eb.b, st)); h->ev_bwd.push_back(eb); }
   unpermute_heads<<<grid_for(n * (long long)c.mlp_out), 256, 0, st>>>(gcm, d_heads, n, c.n_samples, c.head_stride);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail("hr_render_backward: %s", cudaGetErrorString(e));
@@ -990,6 +994,20 @@ int hr_timing_reset(hr_handle* h) {
   if (!h) return fail("null handle");
   drop_events(h->ev_render);
   drop_events(h->ev_mlp);
+  drop_events(h->ev_bwd);
+  return 0;
+}
+
+int hr_timing_read_backward(hr_handle* h, double* backward_ms_avg, int64_t* launches) {
+  if (!h) return fail("null handle");
+  double sb = 0;
+  for (auto& p : h->ev_bwd) {
+    CK(cudaEventSynchronize(p.b));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, p.a, p.b)); sb += ms;
+  }
+  const size_t k = h->ev_bwd.size();
+  if (backward_ms_avg) *backward_ms_avg = k ? sb / k : 0.0;
+  if (launches) *launches = (int64_t)k;
   return 0;
 }
 
@@ -1022,6 +1040,7 @@ int hr_destroy(hr_handle* h) {
   hr::free_mlp_tc2(h);
   drop_events(h->ev_render);
   drop_events(h->ev_mlp);
+  drop_events(h->ev_bwd);
   for (int i = 0; i < 3; ++i) {
     if (i == 0) {
       drop_host_graph(h);

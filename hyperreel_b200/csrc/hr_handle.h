@@ -53,7 +53,7 @@ struct hr_handle {
   size_t g_sizes[13] = {0};   // element counts of the 13 buffers above (to notice a resized grid)
   int64_t launches = 0;
   bool timing = false;
-  std::vector<EventPair> ev_render, ev_mlp;
+  std::vector<EventPair> ev_render, ev_mlp, ev_bwd;
   HostPipe pipe;
 };
 

@@ -382,7 +382,9 @@ class LightfieldModel(nn.Module):
     def timing_read(self):
         r, m, k = C.c_double(), C.c_double(), C.c_int64()
         L.check(self._lib.hr_timing_read(self._handle, C.byref(r), C.byref(m), C.byref(k)))
-        return {"render_ms": r.value, "mlp_ms": m.value, "launches": k.value}
+        b, kb = C.c_double(), C.c_int64()
+        L.check(self._lib.hr_timing_read_backward(self._handle, C.byref(b), C.byref(kb)))
+        return {"render_ms": r.value, "mlp_ms": m.value, "launches": k.value, "backward_ms": b.value, "backward_launches": kb.value}
 
     def launch_count(self) -> int:
         return int(self._lib.hr_launch_count(self._handle)) if self._handle else 0

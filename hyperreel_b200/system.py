@@ -1,10 +1,12 @@
 """Render-path surface of the reference's ``INRSystem`` (nlf/__init__.py:278-502).
 
 Only what sits on the hot path is kept: construction from the full config (``cfg.model``, ``cfg.training``,
-``cfg.dataset``), ``forward`` / ``render`` / ``run_chunked`` with the reference's chunk selection, and
+``cfg.dataset``), ``forward`` / ``render`` / ``run_chunked`` with the reference's chunk selection,
 ``load_state_dict`` with the reference's grid-size fix-up (nlf/__init__.py:433-479), including Lightning
-checkpoints whose keys carry the ``render_fn.`` prefix.  Training, optimisers, regularisers, visualisers
-and datasets are out of scope.
+checkpoints whose keys carry the ``render_fn.`` prefix, and -- SURVEY.md section 8 row f1 -- ``configure_optimizers`` /
+``training_step`` (nlf/__init__.py:504-523, 634-709) over the differentiable path: image loss, manual optimisation with
+one Adam per optimiser group.  Regularisers, the grid up-sampling schedule, visualisers and datasets are out of scope
+(SURVEY.md section 2).
 """
 from __future__ import annotations
 
@@ -51,6 +53,56 @@ class INRSystem(nn.Module):
         else:
             chunk = training.get("ray_chunk", 1 << 20)
         return render_chunked(coords, fn, render_kwargs, chunk=chunk)
+
+    # ---- nlf/__init__.py:504-523 + utils/__init__.py:49-76 (get_optimizer): one Adam(betas=(0.9, 0.99), eps=1e-8) per group
+    OPT_DEFAULTS = {"color": 0.02, "color_impl": 0.001, "embedding_impl": 0.00075}  # conf/experiment/training/*_tensorf.yaml
+
+    def optimizer_groups(self):
+        """Parameters by the reference's `opt_group` names: the VM tables ('color'), basis_mat ('color_impl'), the sample
+        net ('embedding_impl') (nlf/nets/tensorf_base.py opt_group dict, nlf/embedding/ray.py net group)."""
+        model = self.render_fn.model
+        net = model.color_model.net
+        tables = [p for n, p in net.named_parameters() if "plane" in n or "line" in n]
+        impl = [p for n, p in net.named_parameters() if "basis_mat" in n]
+        return {"color": tables, "color_impl": impl, "embedding_impl": list(model.embedding_model.parameters())}
+
+    def configure_optimizers(self):
+        training = self.cfg.get("training", Cfg())
+        ocfg = training.get("optimizers", Cfg())
+        self._optimizers = []
+        for key, params in self.optimizer_groups().items():
+            params = [p for p in params if p.numel() > 0]
+            if not params:
+                continue
+            oc = ocfg.get(key, Cfg())
+            if oc.get("optimizer", "adam") != "adam":
+                raise NotImplementedError("only the reference's default optimizer (adam) is mirrored")
+            self._optimizers.append(torch.optim.Adam(params, lr=float(oc.get("lr", self.OPT_DEFAULTS[key])), eps=1e-8,
+                                                     weight_decay=float(oc.get("weight_decay", 0)), betas=(0.9, 0.99)))
+        return self._optimizers
+
+    def training_step(self, batch, batch_idx: int = 0):
+        """One iteration of nlf/__init__.py:634-709 on this path: batch {'coords' [N,C], 'rgb' [N,3], optional 'weight'};
+        loss = MSE(rgb_pred * w, rgb * w) (losses.py 'mse'), manual optimisation (zero_grad / backward / step per group)."""
+        if not getattr(self, "_optimizers", None):
+            self.configure_optimizers()
+        self.train()
+        coords, rgb = batch["coords"], batch["rgb"]
+        weight = batch.get("weight", None)
+        results = self(coords)
+        pred = results["rgb"]
+        if weight is not None:
+            loss = torch.mean((pred * weight - rgb * weight) ** 2)
+        else:
+            loss = torch.mean((pred - rgb) ** 2)
+        for opt in self._optimizers:
+            opt.zero_grad(set_to_none=True)
+        loss.backward()
+        for opt in self._optimizers:
+            opt.step()
+        with torch.no_grad():
+            psnr = -10.0 * torch.log10(torch.mean((pred.detach() - rgb) ** 2))  # metrics.py:37-45
+        return {"train/loss": loss.detach(), "train/psnr": psnr}
 
     # ---- nlf/__init__.py:433-479
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = False):

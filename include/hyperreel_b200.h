@@ -338,6 +338,8 @@ int64_t hr_launch_count(const hr_handle* h);
 int hr_timing_enable(hr_handle* h, int enable);
 int hr_timing_reset(hr_handle* h);
 int hr_timing_read(hr_handle* h, double* render_ms_avg, double* mlp_ms_avg, int64_t* launches);
+/* same for the render-backward kernel of hr_render_backward */
+int hr_timing_read_backward(hr_handle* h, double* backward_ms_avg, int64_t* launches);
 
 /* Replaces: module destruction. */
 int hr_destroy(hr_handle* h);
