@@ -479,10 +479,36 @@ int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
   return 0;
 }
 
-int64_t hr_workspace_bytes(const hr_handle* h, int64_t n_rays) {
-  if (!h || n_rays < 0) return -1;
+// bytes of a heads scratch for n rays: one [mlp_out] fp32 row per ray
+static int64_t heads_bytes(const hr_handle* h, int64_t n_rays) {
   int64_t b = n_rays * (int64_t)h->cfg.mlp_out * (int64_t)sizeof(float);
   return (b + 255) / 256 * 256 + 256;
+}
+
+// hr_render walks a large batch in sub-batches (sample net, then render kernel, per sub-batch) so that the heads scratch
+// stays bounded (0.58 GB at S*15 = 480) instead of growing to 8-21 GB for 4 M-ray batches / full Neural-3D frames.
+// Measured (profiles/r2_notes.md): wave-sized sub-batches that would keep the scratch in L2 cost more in launch ramps than
+// the HBM round trip they save (0.341 vs 0.288 ms per 65 536 rays); 16 tile waves per sub-batch cost ~1.5 % at 1 M rays.
+static int64_t sub_batch_rays(const hr_handle* h) {
+  if (h->sub_rays > 0) return h->sub_rays;
+  return (int64_t)h->num_sms * 128 * 16;
+}
+
+int64_t hr_workspace_bytes(const hr_handle* h, int64_t n_rays) {
+  if (!h || n_rays < 0) return -1;
+  const int64_t sub = sub_batch_rays(h);
+  return heads_bytes(h, (h->sub_rays < 0 || n_rays < sub) ? n_rays : sub);
+}
+
+int64_t hr_train_workspace_bytes(const hr_handle* h, int64_t n_rays) {
+  if (!h || n_rays < 0) return -1;
+  return 2 * heads_bytes(h, n_rays);
+}
+
+int hr_set_sub_batch(hr_handle* h, int64_t rays) {
+  if (!h) return fail("hr_set_sub_batch: null handle");
+  h->sub_rays = rays;
+  return 0;
 }
 
 // The cached hr_render_host graph holds kernel parameters by value: drop it whenever they may have changed.
@@ -526,30 +552,54 @@ static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, f
   if (((uintptr_t)workspace & 15) != 0) return fail("hr_render: workspace must be 16-byte aligned");
   float* heads = (float*)workspace;
   const hr_config& c = h->cfg;
-  EventPair em{nullptr, nullptr}, er{nullptr, nullptr};
   const bool timing = h->timing && h->ev_render.size() < 8192;
-  if (timing) {
-    CK(cudaEventCreate(&em.a)); CK(cudaEventCreate(&em.b)); CK(cudaEventCreate(&er.a)); CK(cudaEventCreate(&er.b));
-    CK(cudaEventRecord(em.a, st));
-  }
-  cudaError_t e;
-  int rc0 = launch_sample_net(h, rays, n, heads, st);
-  if (rc0) return rc0;
-  if (timing) { CK(cudaEventRecord(em.b, st)); CK(cudaEventRecord(er.a, st)); }
-  e = hr::launch_render(c, h->dv, h->tabs, rays, heads, scatter ? *scatter : one_dst(rgb), n, so, h->num_sms, st, rgb8);
-  if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
-  if (timing) {
-    CK(cudaEventRecord(er.b, st));
-    h->ev_mlp.push_back(em);
-    h->ev_render.push_back(er);
-  }
-  h->launches += 1;
-  if (mlp_out) {
-    unpermute_heads<<<grid_for(n * (long long)c.mlp_out), 256, 0, st>>>(heads, mlp_out, n, c.n_samples, c.head_stride);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail("unpermute launch failed: %s", cudaGetErrorString(e));
+  const int64_t sub = (h->sub_rays < 0) ? n : sub_batch_rays(h);
+  for (int64_t off = 0; off < n; off += sub) {
+    const int64_t m = (n - off < sub) ? (n - off) : sub;
+    const float* r = rays + off * c.c_in;
+    EventPair em{nullptr, nullptr}, er{nullptr, nullptr};
+    if (timing) {
+      CK(cudaEventCreate(&em.a)); CK(cudaEventCreate(&em.b)); CK(cudaEventCreate(&er.a)); CK(cudaEventCreate(&er.b));
+      CK(cudaEventRecord(em.a, st));
+    }
+    int rc0 = launch_sample_net(h, r, m, heads, st);
+    if (rc0) return rc0;
+    if (timing) { CK(cudaEventRecord(em.b, st)); CK(cudaEventRecord(er.a, st)); }
+    hr::RgbDst d = scatter ? *scatter : one_dst(rgb);
+    d.row0 += off;
+    hr::ExtraOut so_off;
+    if (so) {  // every extra output is indexed by ray: advance the pointers to this sub-batch
+      so_off = *so;
+      const int64_t S = c.n_samples;
+      if (so_off.distances) so_off.distances += off * S;
+      if (so_off.points) so_off.points += off * S * 3;
+      if (so_off.sigma) so_off.sigma += off * S;
+      if (so_off.weights) so_off.weights += off * S;
+      if (so_off.rgb_samples) so_off.rgb_samples += off * S * 3;
+      for (int f = 0; f < HR_N_FIELDS; ++f) {
+        if (!so_off.field_out[f]) continue;
+        const bool three = f == HR_FIELD_POINTS || f == HR_FIELD_VIEWDIRS || f == HR_FIELD_COLOR_SCALE || f == HR_FIELD_COLOR_SHIFT ||
+                           f == HR_FIELD_SPATIAL_FLOW || f == HR_FIELD_POINT_OFFSET || f == HR_FIELD_COLOR_SCALE_GLOBAL ||
+                           f == HR_FIELD_COLOR_SHIFT_GLOBAL;
+        so_off.field_out[f] += off * (three ? 3 : 1) * (so_off.field_mode[f] == HR_FIELD_NO_OVER ? S : 1);
+      }
+    }
+    cudaError_t e = hr::launch_render(c, h->dv, h->tabs, r, heads, d, m, so ? &so_off : nullptr, h->num_sms, st, rgb8 ? rgb8 + off * 3 : nullptr);
+    if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
+    if (timing) {
+      CK(cudaEventRecord(er.b, st));
+      h->ev_mlp.push_back(em);
+      h->ev_render.push_back(er);
+    }
     h->launches += 1;
+    if (mlp_out) {
+      unpermute_heads<<<grid_for(m * (long long)c.mlp_out), 256, 0, st>>>(heads, mlp_out + off * c.mlp_out, m, c.n_samples, c.head_stride);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return fail("unpermute launch failed: %s", cudaGetErrorString(e));
+      h->launches += 1;
+    }
   }
+  if (timing) h->timed_calls += 1;
   return 0;
 }
 
@@ -647,7 +697,7 @@ int hr_render_frame_to8b_host(hr_handle* h, const hr_camera* cam, uint8_t* rgb8_
       P.d_rays[i] = P.d_rgb[i] = nullptr; P.d_ws[i] = nullptr;
       if (!P.streams[i]) CK(cudaStreamCreateWithFlags(&P.streams[i], cudaStreamNonBlocking));
     }
-    P.ws_bytes = hr_workspace_bytes(h, chunk);
+    P.ws_bytes = heads_bytes(h, chunk);
     for (int i = 0; i < 3; ++i) {
       CK(cudaMalloc((void**)&P.d_rays[i], (size_t)chunk * c.c_in * sizeof(float)));
       CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)chunk * 3 * sizeof(float)));
@@ -704,7 +754,7 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
       P.d_rays[i] = P.d_rgb[i] = nullptr; P.d_ws[i] = nullptr;
       if (!P.streams[i]) CK(cudaStreamCreateWithFlags(&P.streams[i], cudaStreamNonBlocking));
     }
-    P.ws_bytes = hr_workspace_bytes(h, alloc);
+    P.ws_bytes = heads_bytes(h, alloc);
     for (int i = 0; i < 3; ++i) {
       CK(cudaMalloc((void**)&P.d_rays[i], (size_t)alloc * c.c_in * sizeof(float)));
       CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)alloc * 3 * sizeof(float)));
@@ -888,7 +938,7 @@ int hr_render_heads(hr_handle* h, const float* rays, const float* heads, int64_t
   if (!h || !rays || !heads || !rgb || !opts || !workspace) return fail("hr_render_heads: null argument");
   if (!h->uploaded) return fail("hr_render_heads: parameters not uploaded");
   if (n == 0) return 0;
-  if (workspace_bytes < hr_workspace_bytes(h, n)) return fail("hr_render_heads: workspace too small");
+  if (workspace_bytes < heads_bytes(h, n)) return fail("hr_render_heads: workspace too small");
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   hr_config c = h->cfg;
@@ -909,13 +959,13 @@ int hr_render_backward(hr_handle* h, const float* rays, const float* heads, int6
   if (!h->uploaded) return fail("hr_render_backward: parameters not uploaded");
   if (train_supported(h->cfg)) return 1;
   if (n == 0) return 0;
-  if (workspace_bytes < 2 * hr_workspace_bytes(h, n)) return fail("hr_render_backward: workspace too small (2 x hr_workspace_bytes)");
+  if (workspace_bytes < 2 * heads_bytes(h, n)) return fail("hr_render_backward: workspace too small (hr_train_workspace_bytes)");
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const hr_config& c = h->cfg;
   if (ensure_grad_tables(h, st)) return 1;
   float* hcm = (float*)workspace;
-  float* gcm = (float*)((char*)workspace + hr_workspace_bytes(h, n));
+  float* gcm = (float*)((char*)workspace + heads_bytes(h, n));
   permute_heads<<<grid_for(n * (long long)c.mlp_out), 256, 0, st>>>(heads, hcm, n, c.n_samples, c.head_stride);
   const int white = opts->white_bg ? 1 : 0;
   EventPair eb{nullptr, nullptr};
@@ -995,6 +1045,7 @@ int hr_timing_reset(hr_handle* h) {
   drop_events(h->ev_render);
   drop_events(h->ev_mlp);
   drop_events(h->ev_bwd);
+  h->timed_calls = 0;
   return 0;
 }
 
@@ -1022,10 +1073,11 @@ int hr_timing_read(hr_handle* h, double* render_ms_avg, double* mlp_ms_avg, int6
     CK(cudaEventSynchronize(p.b));
     float ms = 0; CK(cudaEventElapsedTime(&ms, p.a, p.b)); sm += ms;
   }
-  size_t k = h->ev_render.size();
+  // per hr_render call: a call may run several sub-batches, i.e. several launches of each kernel
+  const size_t k = h->timed_calls;
   if (render_ms_avg) *render_ms_avg = k ? sr / k : 0.0;
   if (mlp_ms_avg) *mlp_ms_avg = k ? sm / k : 0.0;
-  if (launches) *launches = (int64_t)k;
+  if (launches) *launches = (int64_t)h->ev_render.size();
   return 0;
 }
 

@@ -53,6 +53,8 @@ struct hr_handle {
   size_t g_sizes[13] = {0};   // element counts of the 13 buffers above (to notice a resized grid)
   int64_t launches = 0;
   bool timing = false;
+  size_t timed_calls = 0;      // hr_render calls covered by ev_render / ev_mlp (a call may run several sub-batches)
+  int64_t sub_rays = 0;        // rays per sub-batch of hr_render: 0 = 16 tile waves (default), < 0 = never split
   std::vector<EventPair> ev_render, ev_mlp, ev_bwd;
   HostPipe pipe;
 };

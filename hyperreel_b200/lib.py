@@ -123,6 +123,8 @@ EXPORTS = {
     "hr_create": (C.c_int, [C.POINTER(hr_config), C.c_int, C.POINTER(C.c_void_p)]),
     "hr_upload": (C.c_int, [C.c_void_p, C.POINTER(hr_params), C.c_void_p]),
     "hr_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "hr_train_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "hr_set_sub_batch": (C.c_int, [C.c_void_p, C.c_int64]),
     "hr_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hr_render_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p,
                                      C.c_int64, C.c_void_p]),

@@ -219,7 +219,7 @@ class LightfieldModel(nn.Module):
         return (rgb, x) if return_heads else rgb  # x: the sample-net output [N, S*stride] (gradient bisecting)
 
     def _train_workspace(self, n, dev):
-        need = 2 * int(self._lib.hr_workspace_bytes(self._handle, n))
+        need = int(self._lib.hr_train_workspace_bytes(self._handle, n))
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         return self._ws
@@ -386,6 +386,12 @@ class LightfieldModel(nn.Module):
         L.check(self._lib.hr_timing_read_backward(self._handle, C.byref(b), C.byref(kb)))
         return {"render_ms": r.value, "mlp_ms": m.value, "launches": k.value, "backward_ms": b.value, "backward_launches": kb.value}
 
+    def set_sub_batch(self, rays: int):
+        """Rays per sub-batch of the render call (0 = 16 sample-net tile waves, the default; < 0 = never split)."""
+        self._sub_batch = int(rays)
+        if self._handle:
+            L.check(self._lib.hr_set_sub_batch(self._handle, self._sub_batch))
+
     def launch_count(self) -> int:
         return int(self._lib.hr_launch_count(self._handle)) if self._handle else 0
 
@@ -446,6 +452,8 @@ class LightfieldModel(nn.Module):
         if not self._handle or self._device_index != idx:
             self._release_handle()
             L.check(self._lib.hr_create(C.byref(self.sig.cfg), idx, C.byref(self._handle)))
+            if getattr(self, "_sub_batch", 0):
+                L.check(self._lib.hr_set_sub_batch(self._handle, self._sub_batch))
             self._device_index = idx
             self._uploaded_version = None
         P = L.hr_params()

@@ -184,8 +184,13 @@ int hr_create(const hr_config* cfg, int device, hr_handle** out);
  * state_dict (any grid size: sizes come from the tensors, Appendix B), pack for the kernels. */
 int hr_upload(hr_handle* h, const hr_params* p, void* stream);
 
-/* Bytes of scratch hr_render needs for n rays (per-ray sample-net outputs). */
+/* Bytes of scratch hr_render needs for n rays (per-ray sample-net outputs).  Bounded: hr_render walks a large batch in
+ * sub-batches of 16 sample-net tile waves (16 x num_sms x 128 rays), so the scratch never exceeds ~0.6 GB. */
 int64_t hr_workspace_bytes(const hr_handle* h, int64_t n_rays);
+/* Scratch of hr_render_heads / hr_render_backward (two full [n, mlp_out] buffers). */
+int64_t hr_train_workspace_bytes(const hr_handle* h, int64_t n_rays);
+/* Tuning: rays per sub-batch of hr_render (0 = default: 16 tile waves; < 0 = never split, scratch grows with n). */
+int hr_set_sub_batch(hr_handle* h, int64_t rays);
 
 /* Replaces: RenderLightfield.forward -> LightfieldModel.forward (nlf/rendering.py:72-77,
  * nlf/models/models.py:135-138) for one chunk: rays [n, c_in] fp32 device -> rgb [n,3] fp32 device.
@@ -319,11 +324,11 @@ typedef struct hr_grads {  /* device buffers in the reference's layouts (hr_para
 
 /* enc [n, mlp_in] fp32 device */
 int hr_encode_rays(hr_handle* h, const float* rays, int64_t n_rays, float* enc, void* stream);
-/* heads [n, mlp_out] in the reference's order (sample-major: column s*head_stride + c, ray.py:333); workspace as for
- * hr_render */
+/* heads [n, mlp_out] in the reference's order (sample-major: column s*head_stride + c, ray.py:333); workspace of
+ * hr_train_workspace_bytes(h, n) */
 int hr_render_heads(hr_handle* h, const float* rays, const float* heads, int64_t n_rays, float* rgb, const hr_train_opts* opts,
                     void* workspace, int64_t workspace_bytes, void* stream);
-/* d_rgb [n,3] -> d_heads [n, mlp_out] (reference order); workspace of 2 * hr_workspace_bytes(h, n) */
+/* d_rgb [n,3] -> d_heads [n, mlp_out] (reference order); workspace of hr_train_workspace_bytes(h, n) */
 int hr_render_backward(hr_handle* h, const float* rays, const float* heads, int64_t n_rays, const float* d_rgb, float* d_heads,
                        const hr_train_opts* opts, void* workspace, int64_t workspace_bytes, void* stream);
 int hr_grad_zero(hr_handle* h, void* stream);
