@@ -37,6 +37,21 @@ __device__ __forceinline__ void sort_keys(float (&k)[SPL], int lane) {
   }
 }
 
+// Same for one key per lane within groups of LW consecutive lanes (two rays per warp: LW = 16), e = lane within the group.
+template <int LW>
+__device__ __forceinline__ void sort_keys_sub(float& k, int e) {
+#pragma unroll
+  for (int size = 2; size <= LW; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const float other = __shfl_xor_sync(kFull, k, stride);
+      const bool up = ((e & size) == 0);
+      const bool lower = ((e & stride) == 0);
+      k = (lower == up) ? fminf(k, other) : fmaxf(k, other);
+    }
+  }
+}
+
 // mipnerf inverse contraction of a scalar distance (reference: nlf/contract.py:143-158).
 __device__ __forceinline__ float inv_contract_distance(const hr_config& cfg, const Derived& dv, float d) {
   d = __fmul_rn(__fmul_rn(d, 0.5f), 2.0f);  // distance_activation = identity: (d/2)*2

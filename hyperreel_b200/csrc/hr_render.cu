@@ -11,6 +11,9 @@
 //     LDG.128 (reference: F.grid_sample calls in nlf/nets/tensorf_dynamic.py:287-371 and
 //     nlf/nets/tensorf_no_sample.py:47-126).
 // Nothing per-sample ever goes to HBM: rays (4*c_in B) + sample-net heads in, rgb (12 B) out.
+// Models with S <= 16 samples per ray run two rays per warp (RPW == 2): lanes 16r .. 16r+15 are the samples of ray r in the
+// lane = sample mapping, and the 32 sample slots of the warp feed the four gather rounds exactly like one 32-sample ray, so
+// no lane idles in either mapping (one ray per warp left half of every warp idle at S = 16, the DoNeRF BASELINE config).
 #include "hr_common.cuh"
 #include "hr_geom.cuh"
 
@@ -105,7 +108,7 @@ __device__ __forceinline__ void group_products(const GroupTaps<C, DYN>& g, float
   for (int c = 0; c < 4; ++c) prod[c] = A[c] * B[c];
 }
 
-template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool EXTRA>
+template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool EXTRA, int RPW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (C1 + C2 == 0 || SPL == 1) ? 3 : 2)
 render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Derived dv,
               const __grid_constant__ RenderTabs tabs, const float* __restrict__ rays,
@@ -114,11 +117,14 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
   constexpr int NT = C0 + C1 + C2;
   constexpr int ROWS = (SHADE == HR_SHADE_SH) ? 9 : 1;
   constexpr int ROUNDS = 4 * SPL;
+  constexpr int LW = 32 / RPW;  // lanes (= sample slots) per ray in the lane = sample mapping
+  static_assert(RPW == 1 || (SPL == 1 && !EXTRA), "two rays per warp: S <= 16, plain outputs");
   extern __shared__ float s_basis[];  // [app_dim][NT] copy of basis_mat
   for (int i = threadIdx.x; i < 3 * ROWS * NT; i += blockDim.x) s_basis[i] = tabs.basis[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
+  const int sub = lane / LW, sl = lane % LW;  // ray of this lane within the warp, sample index within the ray
   const int q = lane & 3, xt = q >> 1, alt = q & 1, quad = lane >> 2;
   const int qc = min(q, 2);
   const int S = cfg.n_samples;
@@ -143,10 +149,12 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
 #pragma unroll
     for (int i = 0; i < 4; ++i) { fcol[C0 + C1 + i] = C0 + C1 + alt * 4 + i; fcol[C0 + C1 + 4 + i] = C0 + C1 + (1 - alt) * 4 + i; }
   }
-  float G[NT];  // per-lane row of the (view-folded) appearance matrix: rgb_q = act(sum_i G[i] * f[i])
+  // per-lane row of the (view-folded) appearance matrix of each ray of the warp: rgb_q = act(sum_i G[r][i] * f[i])
+  constexpr int NG = (SHADE == HR_SHADE_SH) ? RPW : 1;
+  float G[NG][NT];
   if constexpr (SHADE == HR_SHADE_RGB) {
 #pragma unroll
-    for (int i = 0; i < NT; ++i) G[i] = s_basis[qc * NT + fcol[i]];
+    for (int i = 0; i < NT; ++i) G[0][i] = s_basis[qc * NT + fcol[i]];
   }
 
   const float inv_x = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[3], cfg.aabb[0]));  // invaabbSize (tensorf_base.py:292)
@@ -154,16 +162,20 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
   const float inv_z = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[5], cfg.aabb[2]));
   const int line_bytes = out_stride * 4;
 
-  for (long long ray = warp0; ray < n_rays; ray += nwarps) {
+  for (long long base = warp0 * RPW; base < n_rays; base += nwarps * RPW) {
+    // this lane's ray; the second ray of the last warp may not exist: it is computed on a copy of the last ray (every lane
+    // takes part in the shuffles) and never stored
+    const bool ray_ok = base + sub < n_rays;
+    const long long ray = ray_ok ? base + sub : n_rays - 1;
     const float* r = rays + ray * cfg.c_in;
     const float* hrow = heads + ray * (long long)out_stride;
     // ---- warm L1 with the next ray's head row (1.9 KB) while this one is processed ----
     {
-      const long long nxt = ray + nwarps;
+      const long long nxt = ray + nwarps * RPW;
       if (nxt < n_rays) {
-        const char* p = reinterpret_cast<const char*>(heads + nxt * (long long)out_stride) + lane * 128;
-        if (lane * 128 < line_bytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-        if (lane == 31) asm volatile("prefetch.global.L1 [%0];" ::"l"(rays + nxt * cfg.c_in));
+        const char* p = reinterpret_cast<const char*>(heads + nxt * (long long)out_stride) + sl * 128;
+        if (sl * 128 < line_bytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+        if (sl == LW - 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(rays + nxt * cfg.c_in));
       }
     }
     const float ox = __ldg(r + 0), oy = __ldg(r + 1), oz = __ldg(r + 2);
@@ -174,7 +186,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     float hz[SPL][4], hfl[SPL][3], hsg[SPL], hsp[SPL], hof[SPL][3];
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
-      const int s = lane + 32 * j;
+      const int s = sl + 32 * j;
       const float* hp = hrow + ((s < S) ? s : 0);
 #pragma unroll
       for (int c = 0; c < 4; ++c) hz[j][c] = (c < cfg.n_z) ? __ldg(hp + (cfg.off_z + c) * S) : 0.0f;
@@ -202,12 +214,13 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     if constexpr (SHADE == HR_SHADE_SH) {
       float Y[9];
       sh_basis9(dx, dy, dz, Y);  // viewdirs = rays[:,3:6] as given (point.py:866-867)
-      // the 3*NT entries are built once, spread over the lanes, then every lane collects its row in its column order
-      constexpr int GE = 3 * NT, GM = (GE + 31) / 32;
+      // the 3*NT entries of a ray are built once, spread over its LW lanes, then every lane of the warp collects its row of
+      // every ray's matrix in its column order (the quad mapping works on samples of all rays of the warp)
+      constexpr int GE = 3 * NT, GM = (GE + LW - 1) / LW;
       float g[GM];
 #pragma unroll
       for (int m = 0; m < GM; ++m) {
-        const int e = min(lane + 32 * m, GE - 1);
+        const int e = min(sl + LW * m, GE - 1);
         const int eq = e / NT, ei = e % NT;
         float a = 0.0f;
 #pragma unroll
@@ -217,13 +230,16 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
 #pragma unroll
       for (int i = 0; i < NT; ++i) {
         const int E = qc * NT + fcol[i];
-        float v = 0.0f;
 #pragma unroll
-        for (int m = 0; m < GM; ++m) {
-          const float t = __shfl_sync(kFull, g[m], E & 31);
-          if ((E >> 5) == m) v = t;
+        for (int rr = 0; rr < RPW; ++rr) {
+          float v = 0.0f;
+#pragma unroll
+          for (int m = 0; m < GM; ++m) {
+            const float t = __shfl_sync(kFull, g[m], rr * LW + (E % LW));
+            if ((E / LW) == m) v = t;
+          }
+          G[rr][i] = v;
         }
-        G[i] = v;
       }
     }
 
@@ -231,7 +247,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     float tkey[SPL], disp[SPL][3];
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
-      const int s = lane + 32 * j;
+      const int s = sl + 32 * j;
       const bool act = s < S;
       const float sg = (cfg.off_sigma >= 0) ? apply_act(cfg.act_sigma, hsg[j]) : 0.0f;
       const float sgp = (cfg.off_point_sigma >= 0) ? apply_act(cfg.act_point_sigma, hsp[j]) : 0.0f;
@@ -354,7 +370,10 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     }
 
     // ---- sort distances only (base.py:206-210) ----
-    if (cfg.isect_sort) sort_keys<SPL>(tkey, lane);
+    if (cfg.isect_sort) {
+      if constexpr (RPW == 1) sort_keys<SPL>(tkey, lane);
+      else sort_keys_sub<LW>(tkey[0], sl);
+    }
 
     // ---- points, contraction, flow, offset, validity, texel coordinates along the three grid axes ----
     float dist[SPL], fx[SPL], fy[SPL], fz[SPL];
@@ -366,7 +385,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     else if (cfg.contract_type == HR_CONTRACT_AFFINE) contract_point_affine(cfg, cocx, cocy, cocz);
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
-      const int s = lane + 32 * j;
+      const int s = sl + 32 * j;
       const bool act = s < S;
       float t = act ? tkey[j] : 0.0f;
       const bool zero = (t == 0.0f);
@@ -422,9 +441,11 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     for (int rd = 0; rd < ROUNDS; ++rd) {
       sig_r[rd] = 0.0f;
       rgb_r[rd] = 0.0f;
-      if (rd * 8 >= S) continue;  // warp-uniform
+      // round rd serves sample slots rd*8 .. rd*8+7 of the warp: samples (rd % (LW/8))*8 .. of ray rd / (LW/8)
+      if ((RPW == 1 ? rd : (rd % (LW / 8))) * 8 >= S) continue;  // warp-uniform
       const int j = rd >> 2;
       const int src = (rd & 3) * 8 + quad;
+      const int krow_s = (RPW == 1) ? krow : __shfl_sync(kFull, krow, src);
       int sx = __shfl_sync(kFull, ix[j], src);
       const int sy = __shfl_sync(kFull, iy[j], src);
       const int sz = __shfl_sync(kFull, iz[j], src);
@@ -436,15 +457,15 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       GroupTaps<C0, DYN> s0, a0;
       GroupTaps<(C1 ? C1 : 4), DYN> s1, a1;
       GroupTaps<(C2 ? C2 : 4), DYN> s2, a2;
-      group_fetch<C0, DYN>(s0, tabs.sig[0], sx, sy, sz, krow, xt, alt, ok);
-      group_fetch<C0, DYN>(a0, tabs.app[0], sx, sy, sz, krow, xt, alt, ok);
+      group_fetch<C0, DYN>(s0, tabs.sig[0], sx, sy, sz, krow_s, xt, alt, ok);
+      group_fetch<C0, DYN>(a0, tabs.app[0], sx, sy, sz, krow_s, xt, alt, ok);
       if constexpr (C1 > 0) {
-        group_fetch<C1, DYN>(s1, tabs.sig[1], sx, sz, sy, krow, xt, alt, ok);
-        group_fetch<C1, DYN>(a1, tabs.app[1], sx, sz, sy, krow, xt, alt, ok);
+        group_fetch<C1, DYN>(s1, tabs.sig[1], sx, sz, sy, krow_s, xt, alt, ok);
+        group_fetch<C1, DYN>(a1, tabs.app[1], sx, sz, sy, krow_s, xt, alt, ok);
       }
       if constexpr (C2 > 0) {
-        group_fetch<C2, DYN>(s2, tabs.sig[2], sy, sz, sx, krow, xt, alt, ok);
-        group_fetch<C2, DYN>(a2, tabs.app[2], sy, sz, sx, krow, xt, alt, ok);
+        group_fetch<C2, DYN>(s2, tabs.sig[2], sy, sz, sx, krow_s, xt, alt, ok);
+        group_fetch<C2, DYN>(a2, tabs.app[2], sy, sz, sx, krow_s, xt, alt, ok);
       }
       // density feature: sum_c space_c * second_c over all groups (tensorf_dynamic.py:330, tensorf_no_sample.py:76-78)
       float f[NT];
@@ -494,7 +515,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       // appearance: basis_mat (tensorf_dynamic.py:371) folded with the shading (tensorf_utils.py:334-343)
       float acc = 0.0f;
 #pragma unroll
-      for (int i = 0; i < NT; ++i) acc = fmaf(G[i], f[i], acc);
+      for (int i = 0; i < NT; ++i) acc = fmaf(G[(NG == 1) ? 0 : rd / (LW / 8)][i], f[i], acc);
       float col;
       if constexpr (SHADE == HR_SHADE_SH) col = fmaxf(acc + 0.5f, 0.0f);
       else col = 1.0f / (1.0f + expf(-acc));
@@ -508,7 +529,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     float csA[SPL][3];
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
-      const int s = lane + 32 * j;
+      const int s = sl + 32 * j;
       const float* hp = hrow + ((s < S) ? s : 0);
       float cs_raw[3] = {0.f, 0.f, 0.f}, csh_raw[3] = {0.f, 0.f, 0.f};
       if (cfg.use_color_scale_shift) {
@@ -537,7 +558,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       float nxt = __shfl_down_sync(kFull, dist[j], 1);
       if (j + 1 < SPL) {
         float first_next = __shfl_sync(kFull, dist[(j + 1 < SPL) ? j + 1 : j], 0);
-        if (lane == 31) nxt = first_next;
+        if (lane == 31) nxt = first_next;  // SPL == 2 only (one ray per warp)
       }
       float delta = (s == S - 1) ? 1e10f : __fsub_rn(nxt, dist[j]);
       float alpha = __fsub_rn(1.0f, expf(-__fmul_rn(sigma, __fmul_rn(delta, cfg.distance_scale))));
@@ -546,12 +567,12 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       if (s >= S) a1 = 1.0f;
       float inc = a1;  // inclusive product scan
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
+      for (int d = 1; d < LW; d <<= 1) {
         float o = __shfl_up_sync(kFull, inc, d);
-        if (lane >= d) inc *= o;
+        if (sl >= d) inc *= o;
       }
       float exc = __shfl_up_sync(kFull, inc, 1);
-      if (lane == 0) exc = 1.0f;
+      if (sl == 0) exc = 1.0f;
       const float T = carryT * exc;
       carryT = carryT * __shfl_sync(kFull, inc, 31);
       const float w = alpha * T;
@@ -633,17 +654,19 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     }
 
     // ---- composite: sum_s w_s * (rgb_s*(1+cs_s) + csh_s) (tensorf_dynamic.py:780-792) ----
-    float accq = 0.0f;
+    float accq_r[RPW];  // per ray of the warp: colour channel q summed over the samples this lane's quads served
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) accq_r[rr] = 0.0f;
 #pragma unroll
     for (int rd = 0; rd < ROUNDS; ++rd) {
-      if (rd * 8 >= S) continue;
+      if ((RPW == 1 ? rd : (rd % (LW / 8))) * 8 >= S) continue;
       const int j = rd >> 2;
       const int src = (rd & 3) * 8 + quad;
       const float g0 = __shfl_sync(kFull, csA[j][0], src);
       const float g1 = __shfl_sync(kFull, csA[j][1], src);
       const float g2 = __shfl_sync(kFull, csA[j][2], src);
       const float Aq = (q == 0) ? g0 : ((q == 1) ? g1 : g2);
-      accq = fmaf(Aq, rgb_r[rd], accq);
+      accq_r[(RPW == 1) ? 0 : rd / (LW / 8)] = fmaf(Aq, rgb_r[rd], accq_r[(RPW == 1) ? 0 : rd / (LW / 8)]);
       if constexpr (EXTRA) {
         if (so.rgb_samples != nullptr) {
           const float ws = __shfl_sync(kFull, wgt[j], src);
@@ -652,37 +675,45 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         }
       }
     }
+    // the quads of the whole warp served every ray's samples: reduce over all quads, then each lane keeps its own ray's sum
+    float accq = 0.0f;
 #pragma unroll
-    for (int d = 4; d < 32; d <<= 1) accq += __shfl_xor_sync(kFull, accq, d);
+    for (int rr = 0; rr < RPW; ++rr) {
+      float a = accq_r[rr];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
+      for (int d = 4; d < 32; d <<= 1) a += __shfl_xor_sync(kFull, a, d);
+      if (rr == sub) accq = a;
+    }
+    // lane = sample partial sums: reduce within the ray's LW lanes
+#pragma unroll
+    for (int d = 1; d < LW; d <<= 1) {
       accw += __shfl_xor_sync(kFull, accw, d);
       accB[0] += __shfl_xor_sync(kFull, accB[0], d);
       accB[1] += __shfl_xor_sync(kFull, accB[1], d);
       accB[2] += __shfl_xor_sync(kFull, accB[2], d);
     }
     float v = 0.0f;
-    if (lane < 3) {
-      v = accq + ((lane == 0) ? accB[0] : ((lane == 1) ? accB[1] : accB[2]));
+    if (sl < 3) {  // lanes 0-2 of the ray's lane group hold quad position q = 0, 1, 2 = colour channel (LW is a multiple of 4)
+      v = accq + ((sl == 0) ? accB[0] : ((sl == 1) ? accB[1] : accB[2]));
       if (cfg.white_bg && !cfg.black_bg) v = v + (1.0f - accw);
       if (cfg.off_cscale_global >= 0) {
         // scale_shift_color_one (utils/tensorf_utils.py:275-281): the heads of sample 0 (MLP order) act on the pixel
-        const float gs = apply_act(cfg.act_cscale_global, __ldg(hrow + (long long)(cfg.off_cscale_global + lane) * S));
-        const float gb = apply_act(cfg.act_cshift_global, __ldg(hrow + (long long)(cfg.off_cshift_global + lane) * S));
+        const float gs = apply_act(cfg.act_cscale_global, __ldg(hrow + (long long)(cfg.off_cscale_global + sl) * S));
+        const float gb = apply_act(cfg.act_cshift_global, __ldg(hrow + (long long)(cfg.off_cshift_global + sl) * S));
         v = __fadd_rn(__fmul_rn(v, __fadd_rn(gs, 1.0f)), gb);
       }
       if (cfg.clamp_output) v = fminf(fmaxf(v, 0.0f), 1.0f);
       if (rgb8_out != nullptr) {
         // to8b (utils/__init__.py:47): (255 * clip(x, 0, 1)).astype(uint8) -- truncation
-        rgb8_out[ray * 3 + lane] = (unsigned char)(int)__fmul_rn(255.0f, fminf(fmaxf(v, 0.0f), 1.0f));
+        if (ray_ok) rgb8_out[ray * 3 + sl] = (unsigned char)(int)__fmul_rn(255.0f, fminf(fmaxf(v, 0.0f), 1.0f));
       }
     }
     if (rgb8_out == nullptr) {
-      // lane l stores channel l % 3 into destination l / 3: one store instruction covers every destination buffer
-      // (the local output, or all ranks' gather buffers when the frame is ray-sharded)
-      const float vv = __shfl_sync(kFull, v, lane % 3);
-      const int d = lane / 3;
-      if (d < dst.n) dst.p[d][(dst.row0 + ray) * 3 + (lane % 3)] = vv;
+      // lane l of a ray's group stores channel l % 3 into destination l / 3: one store instruction covers every
+      // destination buffer (the local output, or all ranks' gather buffers when the frame is ray-sharded)
+      const float vv = __shfl_sync(kFull, v, sub * LW + (sl % 3));
+      const int d = sl / 3;
+      if (d < dst.n && ray_ok) dst.p[d][(dst.row0 + ray) * 3 + (sl % 3)] = vv;
     }
   }
 }
@@ -694,16 +725,25 @@ static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const Ren
   constexpr int ROWS = (SHADE == HR_SHADE_SH) ? 9 : 1;
   constexpr int NT = C0 + C1 + C2;
   size_t smem = 3 * (size_t)ROWS * NT * sizeof(float);
-  long long ctas_needed = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+  // two rays per warp when a ray has at most 16 samples (plain outputs, at most 5 destination buffers: 16 lanes / 3)
+  const bool two_rays = (SPL == 1) && cfg.n_samples <= 16 && so == nullptr && rgb.n <= 5;
+  const int rpw = two_rays ? 2 : 1;
+  long long ctas_needed = (n + kWarpsPerCta * rpw - 1) / (kWarpsPerCta * rpw);
   long long grid = ctas_needed < (long long)num_sms * kMinCtasPerSm * 2 ? ctas_needed : (long long)num_sms * kMinCtasPerSm * 2;
   if (grid < 1) grid = 1;
   const dim3 g((unsigned)grid), b(kWarpsPerCta * 32);
   if (so) {
-    render_kernel<SPL, DYN, C0, C1, C2, SHADE, true><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, *so, rgb8);
+    render_kernel<SPL, DYN, C0, C1, C2, SHADE, true, 1><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, *so, rgb8);
     return cudaGetLastError();
   }
   ExtraOut none{};
-  render_kernel<SPL, DYN, C0, C1, C2, SHADE, false><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, none, rgb8);
+  if constexpr (SPL == 1) {
+    if (two_rays) {
+      render_kernel<SPL, DYN, C0, C1, C2, SHADE, false, 2><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, none, rgb8);
+      return cudaGetLastError();
+    }
+  }
+  render_kernel<SPL, DYN, C0, C1, C2, SHADE, false, 1><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, none, rgb8);
   return cudaGetLastError();
 }
 
