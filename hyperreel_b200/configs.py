@@ -223,6 +223,16 @@ def _apply_variant(cfg: Cfg, variant: str) -> None:
                 g.pe = to_cfg({"type": "basic", "n_freqs": int(g.pe.n_freqs), "freq_multiplier": 2.0})
     elif variant == "wide_pe":  # stanford_z_plane_mem.yaml / immersive_cylinder_pe.yaml: more PE bands -> 33..64 input features
         pred.params.ray.pe.n_freqs = 4
+    elif variant == "zero_net":  # technicolor_z_plane_no_sample.yaml:55-57: `net: {type: zero}` -- samples stay on their base planes
+        pred.net.type = "zero"
+    elif variant == "distance":  # catacaustics_distance.yaml:113-134: samples at signed distances from the ray's closest point
+        if it.type != "sphere":
+            raise ValueError("the distance variant starts from a sphere pipeline")
+        it.type = "euclidean_distance_unified"
+        pred.outputs.z_vals.channels = 1
+        for k in ("origin_scale_factor", "max_axis"):
+            if k in it:
+                del it[k]
     elif variant == "bbox":  # technicolor_z_plane_world.yaml:143-147
         it.contract = to_cfg({"type": "bbox", "contract_samples": True, "bbox_min": [-2.0, -2.0, 0.5],
                               "bbox_max": [2.0, 2.0, -2.5]})

@@ -249,17 +249,19 @@ int validate(const hr_config& c) {
   if (c.abi_version != HR_ABI_VERSION) return fail("hr_config.abi_version %d != %d", c.abi_version, HR_ABI_VERSION);
   if (c.c_in != 6 && c.c_in != 8) return fail("unsupported c_in %d (6: static rays, 8: video rays)", c.c_in);
   if (c.n_groups < 1 || c.n_groups > HR_MAX_GROUPS) return fail("unsupported n_groups %d", c.n_groups);
-  if (c.mlp_layers < 2 || c.mlp_layers > HR_MAX_LAYERS) return fail("unsupported mlp_layers %d", c.mlp_layers);
-  if (c.mlp_width != 128 && c.mlp_width != 256) return fail("unsupported mlp_width %d (128 or 256)", c.mlp_width);
+  if (c.mlp_mode != HR_MLP_FP32_SIMT && c.mlp_mode != HR_MLP_BF16X3_TC && c.mlp_mode != HR_MLP_ZERO) return fail("unsupported mlp_mode");
+  const bool has_net = c.mlp_mode != HR_MLP_ZERO;
+  if (has_net && (c.mlp_layers < 2 || c.mlp_layers > HR_MAX_LAYERS)) return fail("unsupported mlp_layers %d", c.mlp_layers);
+  if (has_net && c.mlp_width != 128 && c.mlp_width != 256) return fail("unsupported mlp_width %d (128 or 256)", c.mlp_width);
   if (c.mlp_in < 1 || c.mlp_in > 64) return fail("unsupported mlp_in %d", c.mlp_in);
-  if (c.mlp_skip != -1 && (c.mlp_skip < 1 || c.mlp_skip > c.mlp_layers - 2)) return fail("bad mlp_skip %d", c.mlp_skip);
+  if (has_net && c.mlp_skip != -1 && (c.mlp_skip < 1 || c.mlp_skip > c.mlp_layers - 2)) return fail("bad mlp_skip %d", c.mlp_skip);
   if (c.n_samples < 1 || c.n_samples > HR_MAX_SAMPLES) return fail("unsupported n_samples %d (max %d)", c.n_samples, HR_MAX_SAMPLES);
   if (c.mlp_out != c.n_samples * c.head_stride) return fail("mlp_out %d != S*head_stride %d", c.mlp_out, c.n_samples * c.head_stride);
   if (c.off_z < 0) return fail("z_vals head is required");
-  if (c.isect_type == HR_ISECT_Z_PLANE && c.n_z != 1) return fail("z_plane needs 1 z channel");
+  if ((c.isect_type == HR_ISECT_Z_PLANE || c.isect_type == HR_ISECT_DISTANCE) && c.n_z != 1) return fail("z_plane / euclidean_distance need 1 z channel");
   if ((c.isect_type == HR_ISECT_SPHERE || c.isect_type == HR_ISECT_CYLINDER) && c.n_z != 4) return fail("sphere / cylinder need 4 z channels");
   if (c.isect_type == HR_ISECT_SPHERE_NEW && c.n_z != 8) return fail("sphere_new needs 8 z channels");
-  if (c.isect_type < HR_ISECT_Z_PLANE || c.isect_type > HR_ISECT_SPHERE_NEW) return fail("unsupported intersect type %d", c.isect_type);
+  if (c.isect_type < HR_ISECT_Z_PLANE || c.isect_type > HR_ISECT_DISTANCE) return fail("unsupported intersect type %d", c.isect_type);
   if (c.contract_type != HR_CONTRACT_NONE && c.contract_type != HR_CONTRACT_MIPNERF && c.contract_type != HR_CONTRACT_AFFINE)
     return fail("unsupported contract type");
   if (c.contract_type == HR_CONTRACT_AFFINE) {
@@ -281,7 +283,6 @@ int validate(const hr_config& c) {
   if (c.shading == HR_SHADE_SH && c.app_dim != 27) return fail("SH shading needs app_dim 27");
   if (c.shading == HR_SHADE_RGB && c.app_dim != 3) return fail("RGB shading needs app_dim 3");
   if (c.shading != HR_SHADE_SH && c.shading != HR_SHADE_RGB) return fail("unsupported shading");
-  if (c.mlp_mode != HR_MLP_FP32_SIMT && c.mlp_mode != HR_MLP_BF16X3_TC) return fail("unsupported mlp_mode");
   return 0;
 }
 
@@ -358,7 +359,7 @@ int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
   h->simt.skip = c.mlp_skip;
   const float* w_dev[HR_MAX_LAYERS] = {nullptr};
   const float* b_dev[HR_MAX_LAYERS] = {nullptr};
-  for (int l = 0; l < L && !rc; ++l) {
+  for (int l = 0; l < L && !rc && c.mlp_mode != HR_MLP_ZERO; ++l) {
     if (!p->mlp_weight[l] || !p->mlp_bias[l]) { rc = fail("hr_upload: mlp layer %d missing", l); break; }
     const bool first = (l == 0), last = (l == L - 1), skip = (l == c.mlp_skip);
     const int in_src = first ? c.mlp_in : (skip ? c.mlp_in + W : W);
@@ -522,6 +523,11 @@ static void drop_host_graph(hr_handle* h) {
 static int launch_sample_net(hr_handle* h, const float* rays, int64_t n, float* heads, cudaStream_t st) {
   const hr_config& c = h->cfg;
   cudaError_t e;
+  if (c.mlp_mode == HR_MLP_ZERO) {  // ZeroMLP (nlf/nets/mlp.py:29-30): x.new_zeros(N, out_channels)
+    e = cudaMemsetAsync(heads, 0, (size_t)n * c.mlp_out * sizeof(float), st);
+    if (e != cudaSuccess) return fail("heads memset failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
   if (c.mlp_mode == HR_MLP_BF16X3_TC) {
     if (!h->tc_ready) return fail("hr_render: tensor-core pack missing");
     e = hr::launch_mlp_tc2(c, h->tc, h->tma_encode, rays, heads, n, h->num_sms, st);
@@ -888,6 +894,7 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
 // ---- backward pass ----
 static int train_supported(const hr_config& c) {
   if (c.isect_type == HR_ISECT_SPHERE_NEW) return fail("backward: the sphere_new primitive is not supported yet");
+  if (c.mlp_mode == HR_MLP_ZERO) { /* no sample net: d heads is simply unused by the caller */ }
   if ((c.isect_type == HR_ISECT_SPHERE || c.isect_type == HR_ISECT_CYLINDER) && c.sphere_origin_scale != 0.0f)
     return fail("backward: learned primitive origins (origin_scale_factor != 0) are not supported yet");
   if (c.contract_type == HR_CONTRACT_AFFINE) return fail("backward: bbox / z_depth contraction is not supported yet");

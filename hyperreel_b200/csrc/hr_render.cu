@@ -243,6 +243,23 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       }
     }
 
+    // ---- euclidean_distance_unified (primitive.py:126-180): samples are distances from the ray's point closest to the
+    // origin, base = d^ x (o x d^) (pluecker_pos, param.py:297-307); per ray: signed distance from o to that point
+    float base_distance = 0.0f;
+    if (cfg.isect_type == HR_ISECT_DISTANCE) {
+      const float nd = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
+      const float vx = __fdiv_rn(dx, nd), vy = __fdiv_rn(dy, nd), vz = __fdiv_rn(dz, nd);
+      const float mx = __fsub_rn(__fmul_rn(oy, vz), __fmul_rn(oz, vy));
+      const float my = __fsub_rn(__fmul_rn(oz, vx), __fmul_rn(ox, vz));
+      const float mz = __fsub_rn(__fmul_rn(ox, vy), __fmul_rn(oy, vx));
+      const float ex = __fsub_rn(__fsub_rn(__fmul_rn(vy, mz), __fmul_rn(vz, my)), ox);
+      const float ey = __fsub_rn(__fsub_rn(__fmul_rn(vz, mx), __fmul_rn(vx, mz)), oy);
+      const float ez = __fsub_rn(__fsub_rn(__fmul_rn(vx, my), __fmul_rn(vy, mx)), oz);
+      const float dotde = __fadd_rn(__fadd_rn(__fmul_rn(dx, ex), __fmul_rn(dy, ey)), __fmul_rn(dz, ez));
+      const float sgn = (dotde > 0.0f) ? 1.0f : ((dotde < 0.0f) ? -1.0f : 0.0f);
+      base_distance = __fmul_rn(sgn, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez))));
+    }
+
     // ---- lane = sample: intersection (base.py:155-203) ----
     float tkey[SPL], disp[SPL][3];
 #pragma unroll
@@ -262,6 +279,11 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         if (cfg.contract_samples) z = inv_contract_sample(cfg, dv, z);
         float dzg = (fabsf(dz) < 1e-5f) ? 1e12f : dz;  // intersect_utils.py:135-142
         t = __fdiv_rn(__fsub_rn(z, oz), dzg);
+      } else if (cfg.isect_type == HR_ISECT_DISTANCE) {
+        float zr = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, hz[j][0])), one_m);
+        float z = __fadd_rn(__fmul_rn(zr, cfg.z_scale), samp);
+        if (cfg.contract_samples) z = inv_contract_sample(cfg, dv, z);
+        t = __fadd_rn(z, base_distance);  // primitive.py:168-178
       } else if (cfg.isect_type == HR_ISECT_SPHERE_NEW) {
         // IntersectSphereNew (primitive.py:489-546): 8 channels per sample = origin 3, resize 3, offset 1, radius 1.  The
         // last four are read here (the heads row sits in L1) so the other pipelines keep their register budget.

@@ -248,7 +248,21 @@ render_bwd_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__
     float a_z[SPL], one_m[SPL], sg[SPL], sgp[SPL];
     float flowv[SPL][3], offv[SPL][3];  // activated flow (without dt) and offset (without (1 - sigma))
     float dens_o[SPL];
-    const int zc_idx = (cfg.isect_type == HR_ISECT_Z_PLANE) ? 0 : 3;  // the z channel that carries the gradient
+    const int zc_idx = (cfg.isect_type == HR_ISECT_Z_PLANE || cfg.isect_type == HR_ISECT_DISTANCE) ? 0 : 3;  // the z channel that carries the gradient
+    float base_distance = 0.0f;  // euclidean_distance_unified: same per-ray term as the forward kernel (no parameter behind it)
+    if (cfg.isect_type == HR_ISECT_DISTANCE) {
+      const float nd = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
+      const float vx = __fdiv_rn(dx, nd), vy = __fdiv_rn(dy, nd), vz = __fdiv_rn(dz, nd);
+      const float mx = __fsub_rn(__fmul_rn(oy, vz), __fmul_rn(oz, vy));
+      const float my = __fsub_rn(__fmul_rn(oz, vx), __fmul_rn(ox, vz));
+      const float mz = __fsub_rn(__fmul_rn(ox, vy), __fmul_rn(oy, vx));
+      const float ex = __fsub_rn(__fsub_rn(__fmul_rn(vy, mz), __fmul_rn(vz, my)), ox);
+      const float ey = __fsub_rn(__fsub_rn(__fmul_rn(vz, mx), __fmul_rn(vx, mz)), oy);
+      const float ez = __fsub_rn(__fsub_rn(__fmul_rn(vx, my), __fmul_rn(vy, mx)), oz);
+      const float dotde = __fadd_rn(__fadd_rn(__fmul_rn(dx, ex), __fmul_rn(dy, ey)), __fmul_rn(dz, ez));
+      const float sgn = (dotde > 0.0f) ? 1.0f : ((dotde < 0.0f) ? -1.0f : 0.0f);
+      base_distance = __fmul_rn(sgn, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez))));
+    }
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
       const int s = lane + 32 * j;
@@ -273,6 +287,12 @@ render_bwd_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__
         const float dzg = (fabsf(dz) < 1e-5f) ? 1e12f : dz;
         t = __fdiv_rn(__fsub_rn(z, oz), dzg);
         dtdzr = cfg.z_scale * dz_dpre / dzg;
+      } else if (cfg.isect_type == HR_ISECT_DISTANCE) {
+        const float zpre = __fadd_rn(__fmul_rn(zr, cfg.z_scale), samp);
+        float z = zpre, dz_dpre = 1.0f;
+        if (cfg.contract_samples) { z = inv_contract_sample(cfg, dv, zpre); dz_dpre = inv_contract_distance_grad(cfg, dv, zpre); }
+        t = __fadd_rn(z, base_distance);
+        dtdzr = cfg.z_scale * dz_dpre;
       } else {
         // sphere / cylinder with constant origins (origin_scale_factor == 0): only the radius channel moves the primitive
         const float gx = cfg.sphere_origin_initial[0], gy = cfg.sphere_origin_initial[1], gz = cfg.sphere_origin_initial[2];

@@ -11,7 +11,7 @@ import os
 import subprocess
 import threading
 
-HR_ABI_VERSION = 8
+HR_ABI_VERSION = 9
 HR_MAX_GROUPS = 4
 HR_MAX_LAYERS = 10
 HR_MAX_SAMPLES = 64
@@ -19,11 +19,11 @@ HR_MAX_PEERS = 8
 
 ACT_IDENTITY, ACT_SIGMOID, ACT_TANH = 0, 1, 2
 PARAM_IDENTITY, PARAM_TWO_PLANE, PARAM_PLUECKER = 0, 1, 2
-ISECT_Z_PLANE, ISECT_SPHERE, ISECT_CYLINDER, ISECT_SPHERE_NEW = 0, 1, 2, 3
+ISECT_Z_PLANE, ISECT_SPHERE, ISECT_CYLINDER, ISECT_SPHERE_NEW, ISECT_DISTANCE = 0, 1, 2, 3, 4
 CONTRACT_NONE, CONTRACT_MIPNERF, CONTRACT_AFFINE = 0, 1, 2
 SHADE_SH, SHADE_RGB = 0, 1
 DENSE_RELU, DENSE_SOFTPLUS, DENSE_RELU_ABS = 0, 1, 2
-MLP_FP32_SIMT, MLP_BF16X3_TC = 0, 1
+MLP_FP32_SIMT, MLP_BF16X3_TC, MLP_ZERO = 0, 1, 2
 # extra fields of the colour net (hr_render_fields): key of the reference's dict `x` -> HR_FIELD_* id
 FIELDS = {"points": 0, "distances": 1, "base_times": 2, "time_offset": 3, "times": 4, "viewdirs": 5, "weights": 6,
           "color_scale": 7, "color_shift": 8, "spatial_flow": 9, "sigma": 10, "point_sigma": 11, "point_offset": 12,

@@ -204,8 +204,11 @@ class LightfieldModel(nn.Module):
             enc = enc.index_select(1, inv.to(rays.device))
         net = self.embedding_model.embeddings[0].net
         x = enc
-        last = len(net.layers) - 1
-        for i, layer in enumerate(net.layers):  # BaseMLP.forward (mlp.py:159-172)
+        if c.mlp_mode == L.MLP_ZERO:  # ZeroMLP.forward (mlp.py:29-30)
+            x = torch.zeros((n, c.mlp_out), device=rays.device)
+        layers = getattr(net, "layers", [])
+        last = len(layers) - 1
+        for i, layer in enumerate(layers):  # BaseMLP.forward (mlp.py:159-172)
             lin = layer[0] if isinstance(layer, nn.Sequential) else layer
             if i == c.mlp_skip:
                 x = torch.cat([enc, x], -1)
@@ -471,7 +474,7 @@ class LightfieldModel(nn.Module):
         net = self.embedding_model.embeddings[0].net
         perm = list(self.sig.in_perm)
         permuted = perm != list(range(len(perm)))
-        for i, layer in enumerate(net.layers):
+        for i, layer in enumerate(getattr(net, "layers", [])):  # a `zero` sample net has no layers to upload
             lin = layer[0] if isinstance(layer, nn.Sequential) else layer
             w = lin.weight
             if permuted and (i == 0 or i == self.sig.cfg.mlp_skip):

@@ -218,8 +218,11 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
 
     # ------------------------------------------------------------------ sample net (mlp.py:60-178)
     ncfg = pred.net
-    if ncfg.type != "base":
+    if ncfg.type not in ("base", "zero"):
         raise UnsupportedPipeline(f"sample net '{ncfg.type}' is not on the fused path")
+    zero_net = ncfg.type == "zero"  # ZeroMLP (nlf/nets/mlp.py:14-33): every head is 0 before its activation
+    if zero_net:
+        c.mlp_mode = L.MLP_ZERO
     for k in ("pe", "latent_dim", "pad_to", "is_constant", "zero_before_channel", "pe_channels"):
         if k in ncfg:
             raise UnsupportedPipeline(f"sample net option '{k}' is not on the fused path")
@@ -240,11 +243,13 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     head_channels = [int(pred.outputs[k].channels) for k in head_names]
     stride = sum(head_channels)
     c.mlp_in, c.mlp_width, c.mlp_layers = mlp_in, int(ncfg.hidden_channels), depth
-    if c.mlp_width not in (128, 256):
+    if zero_net:
+        pass
+    elif c.mlp_width not in (128, 256):
         raise UnsupportedPipeline(f"sample net hidden width {c.mlp_width} is not on the fused path (128 or 256)")
-    if mlp_in > 64:
+    if mlp_in > 64 and not zero_net:
         raise UnsupportedPipeline(f"sample net input of {mlp_in} encoded features is not on the fused path (<= 64)")
-    if not (2 <= depth <= L.HR_MAX_LAYERS):
+    if not (2 <= depth <= L.HR_MAX_LAYERS) and not zero_net:
         raise UnsupportedPipeline(f"sample net depth {depth} is not on the fused path")
     c.mlp_skip = int(skips[0]) if skips else -1
     c.mlp_out = S * stride
@@ -252,7 +257,7 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     c.n_samples, c.head_stride = S, stride
     W = c.mlp_width
     shapes = []
-    for i in range(depth):
+    for i in range(0 if zero_net else depth):
         fin = mlp_in if i == 0 else (W + mlp_in if i == c.mlp_skip else W)
         fout = c.mlp_out if i == depth - 1 else W
         shapes.append((fout, fin))
@@ -293,7 +298,7 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
             raise UnsupportedPipeline(f"intersect option '{k}' is not on the fused path")
     # `outward_facing` is read by sphere_new / cylinder_new / voxel_grid only (primitive.py:262,447; voxel.py:24): the
     # primitives on the fused path ignore it, exactly like the reference classes they mirror
-    if it.type not in ("z_plane", "sphere", "cylinder", "sphere_new") and _get(it, "outward_facing", False):
+    if it.type not in ("z_plane", "sphere", "cylinder", "sphere_new", "euclidean_distance_unified") and _get(it, "outward_facing", False):
         raise UnsupportedPipeline("intersect option 'outward_facing' is not on the fused path for this primitive")
     if _get(isect, "rays_name", "rays") != "rays":
         raise UnsupportedPipeline("rays_name override")
@@ -359,6 +364,12 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
         for i in range(3):
             c.sphere_origin_initial[i] = float(oi[i])
         c.sphere_origin_scale = float(_get(it, "origin_scale_factor", 0.0))
+    elif it.type == "euclidean_distance_unified":  # IntersectEuclideanDistanceUnified (primitive.py:126-180)
+        c.isect_type = L.ISECT_DISTANCE
+        if use_ds:
+            initial, end = torch.tensor(_get(it, "initial", -ds["far"])), torch.tensor(_get(it, "end", ds["far"]))
+        else:
+            initial, end = torch.tensor(_get(it, "initial", 0.0)), torch.tensor(_get(it, "end", 1.0))
     elif it.type == "sphere_new":  # IntersectSphereNew (primitive.py:440-487)
         c.isect_type = L.ISECT_SPHERE_NEW
         if use_ds:  # :446-452: outward_facing picks the sign of the first sphere
@@ -376,7 +387,7 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
             c.sphere_resize_initial[i] = float(ri[i])
     else:
         raise UnsupportedPipeline(f"intersect '{it.type}' is not on the fused path")
-    need_z = {"z_plane": 1, "sphere_new": 8}.get(it.type, 4)
+    need_z = {"z_plane": 1, "euclidean_distance_unified": 1, "sphere_new": 8}.get(it.type, 4)
     if c.n_z != need_z:
         raise UnsupportedPipeline(f"intersect '{it.type}' needs {need_z} z_vals channel(s), got {c.n_z}")
     initial, end = initial.float(), end.float()

@@ -30,6 +30,9 @@ class _SampleNet(nn.Module):
 
     def __init__(self, shapes: Sequence[tuple]):
         super().__init__()
+        if len(shapes) == 0:  # ZeroMLP (nlf/nets/mlp.py:14-33): one unused Linear(1, 1) named `layer`
+            self.layer = nn.Linear(1, 1)
+            return
         self.layers = nn.ModuleList()
         for i, (fout, fin) in enumerate(shapes):
             lin = nn.Linear(fin, fout)  # PyTorch default init == reference (weight_init: none)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HR_ABI_VERSION 8
+#define HR_ABI_VERSION 9
 
 #define HR_MAX_GROUPS 4   /* ray-parameterisation groups feeding the sample net (ray.py:235-263) */
 #define HR_MAX_LAYERS 10  /* Linear layers of the sample net (mlp.py:127-154) */
@@ -54,7 +54,8 @@ typedef struct hr_encode_group {
   float dir_mult, mom_mult;  /* pluecker multipliers (param.py:236-237)                     */
 } hr_encode_group;
 
-enum { HR_ISECT_Z_PLANE = 0, HR_ISECT_SPHERE = 1, HR_ISECT_CYLINDER = 2, HR_ISECT_SPHERE_NEW = 3 };  /* z.py:16-97, primitive.py:366-438, :181-250, :440-546 */
+enum { HR_ISECT_Z_PLANE = 0, HR_ISECT_SPHERE = 1, HR_ISECT_CYLINDER = 2, HR_ISECT_SPHERE_NEW = 3,
+       HR_ISECT_DISTANCE = 4 };  /* z.py:16-97, primitive.py:366-438, :181-250, :440-546, :126-180 (euclidean_distance_unified) */
 enum { HR_CONTRACT_NONE = 0, HR_CONTRACT_MIPNERF = 1, HR_CONTRACT_AFFINE = 2 };  /* AFFINE: bbox / z_depth (contract.py:65-110) */
 enum { HR_SHADE_SH = 0, HR_SHADE_RGB = 1 };
 enum { HR_DENSE_RELU = 0, HR_DENSE_SOFTPLUS = 1, HR_DENSE_RELU_ABS = 2 };
@@ -62,7 +63,8 @@ enum { HR_DENSE_RELU = 0, HR_DENSE_SOFTPLUS = 1, HR_DENSE_RELU_ABS = 2 };
 /* Sample-net arithmetic.  FP32_SIMT: fp32 FMA on CUDA cores (bit-level closest to the reference's
  * cuBLAS SGEMM).  BF16X3_TC: tcgen05 tensor cores, every fp32 operand split into bf16 hi+lo and the
  * three leading cross products accumulated in fp32 TMEM (error ~2^-16 per product). */
-enum { HR_MLP_FP32_SIMT = 0, HR_MLP_BF16X3_TC = 1 };
+enum { HR_MLP_FP32_SIMT = 0, HR_MLP_BF16X3_TC = 1,
+       HR_MLP_ZERO = 2 /* `net: {type: zero}` (ZeroMLP, nlf/nets/mlp.py:14-33): every head is 0, no network runs */ };
 
 /* The recognised pipeline signature; one struct describes what the
  * reference assembles from conf/experiment/model/<name>.yaml.  Anything the YAML asks for that this

@@ -46,7 +46,7 @@ def test_parameter_gradients_match_reference_autograd(name):
         assert np.abs(probe - g[f"probe/{k}"]).max() <= 1e-3 * scale + 1e-10, k
 
 
-@pytest.mark.parametrize("name", ["technicolor_app", "donerf_app", "neural3d_app"])
+@pytest.mark.parametrize("name", ["technicolor_app", "donerf_app", "neural3d_app", "donerf_distance", "technicolor_zero_net"])
 @pytest.mark.parametrize("white", [False, True])
 def test_training_mode_gradients_match_the_oracle(name, white):
     """training_step semantics (no clamp, optional white background) on the appearance-sensitive cases; every parameter

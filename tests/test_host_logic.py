@@ -180,8 +180,9 @@ def test_shipped_model_yamls_that_lower_to_the_fused_path():
         "technicolor_z_plane_mem", "technicolor_z_plane_small", "technicolor_z_plane_tiny", "technicolor_z_plane_large",
         "technicolor_z_plane_world", "immersive_sphere", "immersive_sphere_test", "immersive_cylinder", "immersive_cylinder_pe",
         "bom_cylinder", "catacaustics_z_plane", "catacaustics_cylinder", "shiny_z_plane", "stanford_llff_z_plane", "immersive_sphere_new", "bom_sphere",
+        "catacaustics_distance",
     }
-    assert len(ok) >= 34
+    assert len(ok) >= 35
     assert expected <= ok, sorted(expected - ok)
 
 
