@@ -261,7 +261,14 @@ int validate(const hr_config& c) {
   if ((c.isect_type == HR_ISECT_Z_PLANE || c.isect_type == HR_ISECT_DISTANCE) && c.n_z != 1) return fail("z_plane / euclidean_distance need 1 z channel");
   if ((c.isect_type == HR_ISECT_SPHERE || c.isect_type == HR_ISECT_CYLINDER) && c.n_z != 4) return fail("sphere / cylinder need 4 z channels");
   if (c.isect_type == HR_ISECT_SPHERE_NEW && c.n_z != 8) return fail("sphere_new needs 8 z channels");
-  if (c.isect_type < HR_ISECT_Z_PLANE || c.isect_type > HR_ISECT_DISTANCE) return fail("unsupported intersect type %d", c.isect_type);
+  if (c.isect_type < HR_ISECT_Z_PLANE || c.isect_type > HR_ISECT_PLANE) return fail("unsupported intersect type %d", c.isect_type);
+  if (c.isect_type == HR_ISECT_VOXEL && (c.n_z != 1 || c.isect_axes != 3 || c.n_samples % 3 != 0))
+    return fail("voxel_grid needs 1 z channel and a multiple of 3 samples");
+  if (c.isect_type == HR_ISECT_PLANE && (c.n_z != 4 || c.isect_axes < 1 || c.isect_axes > 3 || c.n_samples % c.isect_axes != 0))
+    return fail("deformable_voxel_grid needs 4 z channels and 1-3 axes dividing the sample count");
+  if (c.n_color_views < 0) return fail("bad n_color_views");
+  if (c.n_color_views > 0 && c.c_in != 8) return fail("colour transform needs 8-channel rays (camera id = rays[:, -2])");
+  if (c.n_color_views > 0 && c.off_cscale_global >= 0) return fail("colour transform and global colour heads are exclusive");
   if (c.contract_type != HR_CONTRACT_NONE && c.contract_type != HR_CONTRACT_MIPNERF && c.contract_type != HR_CONTRACT_AFFINE)
     return fail("unsupported contract type");
   if (c.contract_type == HR_CONTRACT_AFFINE) {
@@ -460,6 +467,24 @@ int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
           if (e != cudaSuccess) rc = fail("basis copy failed: %s", cudaGetErrorString(e));
           h->tabs.basis = dst;
           h->tabs.n_app_total = n_app_total;
+        }
+      }
+    }
+  }
+  if (!rc) {
+    h->tabs.color_embedding = nullptr;
+    if (c.n_color_views > 0) {
+      if (!p->color_embedding) rc = fail("hr_upload: color_embedding missing (n_color_views = %d)", c.n_color_views);
+      else {
+        const float* d = nullptr;
+        const size_t cnt = (size_t)c.n_color_views * 12;
+        rc = stage_in(p->color_embedding, cnt, p->on_device, st, temps, &d);
+        float* dst = nullptr;
+        if (!rc) rc = dev_alloc(h, (void**)&dst, cnt * sizeof(float));
+        if (!rc) {
+          cudaError_t e = cudaMemcpyAsync(dst, d, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st);
+          if (e != cudaSuccess) rc = fail("color_embedding copy failed: %s", cudaGetErrorString(e));
+          h->tabs.color_embedding = dst;
         }
       }
     }
@@ -899,6 +924,9 @@ static int train_supported(const hr_config& c) {
     return fail("backward: learned primitive origins (origin_scale_factor != 0) are not supported yet");
   if (c.contract_type == HR_CONTRACT_AFFINE) return fail("backward: bbox / z_depth contraction is not supported yet");
   if (c.off_cscale_global >= 0) return fail("backward: per-ray colour heads are not supported yet");
+  if (c.isect_type == HR_ISECT_VOXEL || c.isect_type == HR_ISECT_PLANE) return fail("backward: voxel-grid primitives are not supported yet");
+  if (c.n_color_views > 0) return fail("backward: the per-camera colour transform is not supported yet");
+  if (c.n_samples > 64) return fail("backward: more than 64 samples per ray are not supported yet");
   return 0;
 }
 

@@ -23,6 +23,7 @@ struct RenderTabs {
   PlaneTab app[3];
   const float* basis;  // [app_dim][sum C_app] row-major
   int n_app_total;
+  const float* color_embedding;  // [n_color_views][12] per-camera colour transform + shift (point.py:558-592), or null
 };
 
 // Host-derived scalars (computed in double on the host, then rounded once to fp32, the way the

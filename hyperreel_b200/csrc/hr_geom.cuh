@@ -19,10 +19,19 @@ __device__ __forceinline__ void sort_keys(float (&k)[SPL], int lane) {
 #pragma unroll
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       if (stride >= 32) {
-        // partner lives in the other register of the same lane (SPL == 2, stride == 32, size == 64)
-        float lo = fminf(k[0], k[SPL - 1]), hi = fmaxf(k[0], k[SPL - 1]);
-        k[0] = lo;
-        k[SPL - 1] = hi;
+        // partner lives in another register of the same lane: r ^ (stride / 32); size >= 64, so the direction of element
+        // e = r*32 + lane depends on r only
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) {
+          const int rs = stride >> 5;
+          if ((r & rs) == 0) {
+            const int r2 = (r | rs) < SPL ? (r | rs) : r;
+            const bool up = (((r * 32) & size) == 0);
+            const float lo = fminf(k[r], k[r2]), hi = fmaxf(k[r], k[r2]);
+            k[r] = up ? lo : hi;
+            k[r2] = up ? hi : lo;
+          }
+        }
       } else {
 #pragma unroll
         for (int r = 0; r < SPL; ++r) {

@@ -22,7 +22,7 @@ struct MlpSimtPack {
 
 // tcgen05 path (HR_MLP_BF16X3_TC): see hr_mlp_tc2.cu.  A "pass" is one accumulator's worth of output columns
 // (128 columns of a hidden layer or of the last layer); its weights are stored as n_chunks*2 k-step images.
-#define HR_TC_MAX_PASSES 24
+#define HR_TC_MAX_PASSES 40  // 10 hidden half passes + 28 last-layer parts (S = 256 x 14 channels)
 struct TcPass {
   int layer;        // Linear layer index
   int n;            // output columns of this pass (multiple of 16, <= 256)

@@ -112,7 +112,7 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
     for (long long i = (long long)blockIdx.x * NTHREADS + tid; i < lines; i += (long long)gridDim.x * NTHREADS)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(w + i * 128));
   }
-  for (int i = tid; i < pk.bias_count; i += NTHREADS) s_bias[i] = pk.bias[i];
+  for (int i = tid; i < min(pk.bias_count, BIAS_FLOATS); i += NTHREADS) s_bias[i] = pk.bias[i];
   for (int i = tid; i < (2 * X_BUF_BYTES) / 16; i += NTHREADS)  // encoded-input operands: columns >= mlp_in stay zero
     reinterpret_cast<uint4*>(smem + OFF_X)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_async_smem();
@@ -374,7 +374,7 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
         if (tid == 0) TR(iter, p, 4);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + lane_base + TM_D + db * 128;
-        const float* bias = s_bias + P.bias_off;
+        const float* bias = s_bias + P.bias_off;  // hidden layers always fit the table (pack_mlp_tc2 checks)
         if (!P.is_final) {
           // Hidden half pass: columns [out_col0, out_col0 + 128) of layer l = k-steps 8h .. 8h+7 of A(l+1).  Group g
           // takes the 16 columns of k-step 8h + 2jj + g in sweep jj, so k-steps become ready in consumption order.
@@ -417,6 +417,8 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
         } else {
           // Last layer: 16-column slices go TMEM -> registers -> 32 x 16 box in shared memory (row = lane) -> one TMA tensor
           // store per box (rows past n_rays / columns past mlp_out are clipped by the tensor map).  Two boxes per warp.
+          // biases past the shared-memory table (very wide last layers: S = 256) are read from global memory
+          if (P.bias_off + P.n > BIAS_FLOATS) bias = pk.bias + P.bias_off;
           const int nslice = (P.n + 15) / 16;
           const int last_h = (grp < nslice) ? ((nslice - 1 - grp) / EPI_GROUPS) * EPI_GROUPS + grp : -1;
           if (last_h < 0) { tc_fence_before(); mbar_arrive(bar(BAR_DEMPTY + db)); }
@@ -511,7 +513,7 @@ int pack_mlp_tc2(hr_handle* h, const float* const* w_dev, const float* const* b_
       bytes += (size_t)P.n_chunks * 2 * P.n * 64;
     }
   }
-  if (bias_off > tc2::BIAS_FLOATS) return hr_fail("tensor-core sample net: bias table too large");
+  if ((L - 1) * W > tc2::BIAS_FLOATS) return hr_fail("tensor-core sample net: hidden bias table too large");
   np_.n_passes = np;
   np_.bias_count = bias_off;
   np_.wpack_bytes = (long long)bytes;

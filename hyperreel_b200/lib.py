@@ -11,15 +11,15 @@ import os
 import subprocess
 import threading
 
-HR_ABI_VERSION = 9
+HR_ABI_VERSION = 10
 HR_MAX_GROUPS = 4
 HR_MAX_LAYERS = 10
-HR_MAX_SAMPLES = 64
+HR_MAX_SAMPLES = 256
 HR_MAX_PEERS = 8
 
 ACT_IDENTITY, ACT_SIGMOID, ACT_TANH = 0, 1, 2
 PARAM_IDENTITY, PARAM_TWO_PLANE, PARAM_PLUECKER = 0, 1, 2
-ISECT_Z_PLANE, ISECT_SPHERE, ISECT_CYLINDER, ISECT_SPHERE_NEW, ISECT_DISTANCE = 0, 1, 2, 3, 4
+ISECT_Z_PLANE, ISECT_SPHERE, ISECT_CYLINDER, ISECT_SPHERE_NEW, ISECT_DISTANCE, ISECT_VOXEL, ISECT_PLANE = 0, 1, 2, 3, 4, 5, 6
 CONTRACT_NONE, CONTRACT_MIPNERF, CONTRACT_AFFINE = 0, 1, 2
 SHADE_SH, SHADE_RGB = 0, 1
 DENSE_RELU, DENSE_SOFTPLUS, DENSE_RELU_ABS = 0, 1, 2
@@ -76,6 +76,9 @@ class hr_config(C.Structure):
         ("off_cscale_global", C.c_int32), ("off_cshift_global", C.c_int32),
         ("act_cscale_global", hr_act), ("act_cshift_global", hr_act),
         ("sphere_resize_scale", C.c_float), ("sphere_resize_initial", C.c_float * 3),
+        ("isect_axes", C.c_int32), ("z_scale3", C.c_float * 3), ("isect_outward", C.c_int32), ("isect_max_axis", C.c_int32),
+        ("plane_normal", C.c_float * 9), ("plane_normal_scale", C.c_float),
+        ("n_color_views", C.c_int32), ("act_ctransform", hr_act), ("act_ctshift", hr_act),
     ]
 
 
@@ -90,7 +93,7 @@ class hr_params(C.Structure):
         ("plane_h", C.c_int32 * 3), ("plane_w", C.c_int32 * 3),
         ("sigma_second", C.c_void_p * 3), ("app_second", C.c_void_p * 3),
         ("second_len", C.c_int32 * 3),
-        ("basis_mat", C.c_void_p),
+        ("basis_mat", C.c_void_p), ("color_embedding", C.c_void_p),
     ]
 
 

@@ -32,7 +32,7 @@ def _dataset_facts(system) -> dict:
         return dict(system)
     ds = {}
     td = getattr(getattr(system, "dm", None), "train_dataset", None)
-    for k in ("num_keyframes", "num_frames", "near", "far", "depth_range"):
+    for k in ("num_keyframes", "num_frames", "near", "far", "depth_range", "bbox_min", "bbox_max", "total_images_per_frame", "val_all"):
         if td is not None and hasattr(td, k):
             ds[k] = getattr(td, k)
     dcfg = getattr(getattr(system, "cfg", None), "dataset", None)
@@ -87,7 +87,7 @@ class LightfieldModel(nn.Module):
         self.cur_iter = RENDER_ITER
         grid = kwargs.get("grid") or default_grid(self.sig)
         # reference-named parameter storage
-        self.embedding_model = _Embedding(self.sig.mlp_layer_shapes)
+        self.embedding_model = _Embedding(self.sig.mlp_layer_shapes, self.sig.color_views, self.sig.color_embedding_index)
         self.color_model = _Color(self.sig, grid)
         self._lib = L.load_library()  # raises if the CUDA library is missing -- no fallback
         self._handle = C.c_void_p()
@@ -205,7 +205,7 @@ class LightfieldModel(nn.Module):
         net = self.embedding_model.embeddings[0].net
         x = enc
         if c.mlp_mode == L.MLP_ZERO:  # ZeroMLP.forward (mlp.py:29-30)
-            x = torch.zeros((n, c.mlp_out), device=rays.device)
+            x = torch.zeros((n, c.mlp_out), device=rays.device, requires_grad=return_heads)  # a leaf when the caller bisects d heads
         layers = getattr(net, "layers", [])
         last = len(layers) - 1
         for i, layer in enumerate(layers):  # BaseMLP.forward (mlp.py:159-172)
@@ -494,6 +494,8 @@ class LightfieldModel(nn.Module):
                 P.sigma_plane[i], P.app_plane[i] = dptr(dplane[i]), dptr(aplane[i])
                 P.sigma_second[i], P.app_second[i] = dptr(dsecond[i]), dptr(asecond[i])
         P.basis_mat = dptr(tn.basis_mat.weight)
+        if self.sig.cfg.n_color_views > 0:
+            P.color_embedding = dptr(self.embedding_model.embeddings[self.sig.color_embedding_index].color_embedding)
         stream = torch.cuda.current_stream(torch.device("cuda", idx))
         L.check(self._lib.hr_upload(self._handle, C.byref(P), stream.cuda_stream))
         stream.synchronize()

@@ -43,4 +43,7 @@ def for_signature(sig, n: int, seed: int = 1) -> torch.Tensor:
             g = torch.Generator().manual_seed(seed + 1000)
             r = torch.cat([r, torch.zeros(n, 1), torch.rand(n, 1, generator=g)], -1)
         return r
-    return forward_facing(n, seed, video=(sig.c_in == 8), num_frames=max(int(sig.cfg.num_frames), 1))
+    r = forward_facing(n, seed, video=(sig.c_in == 8), num_frames=max(int(sig.cfg.num_frames), 1))
+    if sig.cfg.n_color_views > 0:  # per-camera colour transform (point.py:594-605): spread the rays over the cameras
+        r[:, 6] = (torch.arange(n) % int(sig.cfg.n_color_views)).float()
+    return r

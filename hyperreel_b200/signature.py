@@ -86,6 +86,10 @@ class Signature:
     # [x | sin(d-major, f-minor) | cos(...)] order differs from WindowedPE's per-band order); applied to the input columns
     # of the first and the skip layer at upload
     in_perm: List[int] = field(default_factory=list)
+    # ColorTransformEmbedding: rows of its `color_embedding` parameter (0 = no such embedding) and its position in the
+    # `embeddings` ModuleList (state_dict name model.embedding_model.embeddings.{index}.color_embedding)
+    color_views: int = 0
+    color_embedding_index: int = -1
 
     @property
     def c_in(self) -> int:
@@ -128,6 +132,10 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
         stop = _get(e, "stop_iters", float("inf"))
         if cur_iter >= wait and cur_iter < stop:  # RayPointEmbedding.forward gate (embedding.py:107)
             seq.append(e)
+    # ColorTransformEmbedding (point.py:558-612) only adds per-ray keys to the dict: it commutes with the point embeddings
+    ctrans = next((e for e in seq if e.type == "color_transform"), None)
+    ctrans_index = next((i for i, k in enumerate(embs.keys()) if embs[k].type == "color_transform"), -1)
+    seq = [e for e in seq if e.type != "color_transform"]
     types = [e.type for e in seq]
     expect = ["ray_prediction", "ray_intersect"]
     rest = types[2:]
@@ -293,12 +301,14 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     for k in ("origin", "weight_fn", "sort_outputs", "dropout", "num_repeat", "use_local_prediction", "flip_axes"):
         if k in it and it[k] not in (False, None, 1):
             raise UnsupportedPipeline(f"intersect option '{k}' is not on the fused path")
-    for k in ("use_disparity", "residual_z", "residual_distance", "normalize", "clamp", "forward_facing", "max_axis"):
+    # (`max_axis` is used by IntersectVoxelGrid only, voxel.py:41,100-110; the other classes ignore the key)
+    for k in ("use_disparity", "residual_z", "residual_distance", "normalize", "clamp", "forward_facing"):
         if _get(it, k, False):
             raise UnsupportedPipeline(f"intersect option '{k}' is not on the fused path")
     # `outward_facing` is read by sphere_new / cylinder_new / voxel_grid only (primitive.py:262,447; voxel.py:24): the
     # primitives on the fused path ignore it, exactly like the reference classes they mirror
-    if it.type not in ("z_plane", "sphere", "cylinder", "sphere_new", "euclidean_distance_unified") and _get(it, "outward_facing", False):
+    if it.type not in ("z_plane", "sphere", "cylinder", "sphere_new", "euclidean_distance_unified", "voxel_grid",
+                       "deformable_voxel_grid") and _get(it, "outward_facing", False):
         raise UnsupportedPipeline("intersect option 'outward_facing' is not on the fused path for this primitive")
     if _get(isect, "rays_name", "rays") != "rays":
         raise UnsupportedPipeline("rays_name override")
@@ -385,32 +395,101 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
         ri = _get(it, "resize_initial", [1.0, 1.0, 1.0])
         for i in range(3):
             c.sphere_resize_initial[i] = float(ri[i])
+    elif it.type in ("voxel_grid", "deformable_voxel_grid"):
+        pass  # per-axis sample tables: built below
     else:
         raise UnsupportedPipeline(f"intersect '{it.type}' is not on the fused path")
-    need_z = {"z_plane": 1, "euclidean_distance_unified": 1, "sphere_new": 8}.get(it.type, 4)
+    need_z = {"z_plane": 1, "euclidean_distance_unified": 1, "sphere_new": 8, "voxel_grid": 1}.get(it.type, 4)
     if c.n_z != need_z:
         raise UnsupportedPipeline(f"intersect '{it.type}' needs {need_z} z_vals channel(s), got {c.n_z}")
-    initial, end = initial.float(), end.float()
-    if c.contract_samples and c.contract_type == L.CONTRACT_AFFINE:  # contract_distance = d / fac (contract.py:80-81,106-107)
-        initial, end = initial / affine_fac, end / affine_fac
-    elif c.contract_samples:
-        initial = _contract_distance(initial, c.contract_start_distance, c.contract_end_distance)
-        end = _contract_distance(end, c.contract_start_distance, c.contract_end_distance)
     if S > L.HR_MAX_SAMPLES:
         raise UnsupportedPipeline(f"z_channels {S} > {L.HR_MAX_SAMPLES}")
-    samples = torch.linspace(float(initial), float(end), S)
-    for i in range(S):
-        c.samples[i] = float(samples[i])
-    # z.py:58-71 (the primitives take cfg.z_scale or the sample spacing: primitive.py:211-219)
-    if "z_scale" in it:
-        c.z_scale = float(it.z_scale)
-    elif S > 1:
-        zs = torch.abs(samples[1] - samples[0])
-        if "num_samples_for_scale" in it and it.type == "z_plane":
-            zs = zs * (S / float(it.num_samples_for_scale))
-        c.z_scale = float(zs)
+
+    def contract_bound(v):
+        v = v.float()
+        if c.contract_samples and c.contract_type == L.CONTRACT_AFFINE:  # contract_distance = d / fac (contract.py:80-81,106-107)
+            return v / affine_fac
+        if c.contract_samples:
+            return _contract_distance(v, c.contract_start_distance, c.contract_end_distance)
+        return v
+
+    c.isect_axes, c.isect_outward, c.isect_max_axis = 1, 0, 0
+    c.plane_normal_scale = 0.0
+    for i in range(9):
+        c.plane_normal[i] = 0.0
+    if it.type in ("voxel_grid", "deformable_voxel_grid"):
+        # IntersectVoxelGrid / IntersectDeformableVoxelGrid constructors (voxel.py:19-75, :115-176): sample s is plane s // A
+        # of axis s % A, one linspace per axis
+        deform = it.type == "deformable_voxel_grid"
+        if _get(it, "use_local_prediction", False):
+            raise UnsupportedPipeline("voxel_grid: use_local_prediction is not on the fused path")
+        if deform:
+            if use_ds:
+                raise UnsupportedPipeline("deformable_voxel_grid with dataset bounds needs the dataset's point cloud")
+            normals = [list(map(float, r)) for r in _get(it, "start_normal", [[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])]
+            A = len(normals)
+            if not (1 <= A <= 3) or any(len(r) != 3 for r in normals):
+                raise UnsupportedPipeline("deformable_voxel_grid: 1 to 3 start normals")
+            for a_ in range(A):
+                for k in range(3):
+                    c.plane_normal[a_ * 3 + k] = normals[a_][k]
+            c.plane_normal_scale = float(_get(it, "normal_scale_factor", 0.1))
+            c.isect_type = L.ISECT_PLANE
+            lo = torch.tensor([float(v) for v in _get(it, "initial", [0.0, 0.0, 0.0])])
+            hi = torch.tensor([float(v) for v in _get(it, "end", [1.0, 1.0, 1.0])])
+        else:
+            A = 3
+            c.isect_type = L.ISECT_VOXEL
+            c.isect_outward = int(bool(_get(it, "outward_facing", False)))
+            c.isect_max_axis = int(bool(_get(it, "max_axis", False)))
+            fac = float(_get(it, "fac", 1.0))
+            if use_ds and not ("initial" in it and "end" in it):
+                if "bbox_min" not in ds or "bbox_max" not in ds:
+                    raise UnsupportedPipeline("voxel_grid with use_dataset_bounds needs the dataset's bbox_min / bbox_max")
+            if use_ds:  # voxel.py:27-29
+                lo = torch.tensor([float(v) for v in it.initial]) if "initial" in it else torch.tensor([float(v) * fac for v in ds["bbox_min"]])
+                hi = torch.tensor([float(v) for v in it.end]) if "end" in it else torch.tensor([float(v) * fac for v in ds["bbox_max"]])
+            else:
+                lo = torch.tensor([float(v) for v in _get(it, "initial", [0.0, 0.0, 0.0])])
+                hi = torch.tensor([float(v) for v in _get(it, "end", [1.0, 1.0, 1.0])])
+        if S % A != 0 or lo.numel() < A or hi.numel() < A:
+            raise UnsupportedPipeline(f"{it.type}: z_channels {S} must be a multiple of the {A} axes, with one bound per axis")
+        lo, hi = contract_bound(lo), contract_bound(hi)
+        P = S // A
+        tab = torch.stack([torch.linspace(float(lo[a_]), float(hi[a_]), P) for a_ in range(A)], -1)  # [P, A]
+        flat = tab.reshape(-1)
+        for i in range(S):
+            c.samples[i] = float(flat[i])
+        if "z_scale" in it:
+            zs = torch.tensor([float(v) for v in it.z_scale])
+            if zs.numel() != (1 if deform else 3):
+                raise UnsupportedPipeline(f"{it.type}: z_scale must have {1 if deform else 3} entries")
+        elif P > 1:
+            zs = torch.abs(flat[1:2] - flat[0:1]) if deform else torch.abs(tab[1] - tab[0])  # voxel.py:169-174 / :58-63
+        else:
+            zs = torch.ones(1 if deform else 3)
+        zs = torch.where(zs == 0.0, torch.ones_like(zs), zs)
+        c.isect_axes = A
+        c.z_scale = float(zs[0])
+        for a_ in range(3):
+            c.z_scale3[a_] = float(zs[a_]) if (not deform) else float(zs[0])
     else:
-        c.z_scale = 1.0
+        initial, end = contract_bound(initial), contract_bound(end)
+        samples = torch.linspace(float(initial), float(end), S)
+        for i in range(S):
+            c.samples[i] = float(samples[i])
+        # z.py:58-71 (the primitives take cfg.z_scale or the sample spacing: primitive.py:211-219)
+        if "z_scale" in it:
+            c.z_scale = float(it.z_scale)
+        elif S > 1:
+            zs = torch.abs(samples[1] - samples[0])
+            if "num_samples_for_scale" in it and it.type == "z_plane":
+                zs = zs * (S / float(it.num_samples_for_scale))
+            c.z_scale = float(zs)
+        else:
+            c.z_scale = 1.0
+        for a_ in range(3):
+            c.z_scale3[a_] = c.z_scale
     c.isect_near = float(_get(it, "near", ds["near"] if use_ds else 0.0))
     c.isect_far = float(_get(it, "far", float("inf")))
     if "mask" in it and it.mask is not None and cur_iter > float(_get(it.mask, "stop_iters", float("inf"))):
@@ -472,6 +551,27 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     c.off_cscale_global = offs["color_scale_global"] if glob[0] else -1
     c.off_cshift_global = offs["color_shift_global"] if glob[0] else -1
     c.act_cscale_global, c.act_cshift_global = act_of("color_scale_global"), act_of("color_shift_global")
+    # per-camera colour transform (ColorTransformEmbedding point.py:558-612 -> transform_color_one tensorf_utils.py:308-331):
+    # active iff the dataset validates on every camera (val_all), the keys pass extract_fields and no color_scale_global exists
+    c.n_color_views = 0
+    c.act_ctransform, c.act_ctshift = L.hr_act(0, 1.0, 0.0, 1.0), L.hr_act(0, 1.0, 0.0, 1.0)
+    color_views = 0
+    if ctrans is not None:
+        if "total_images_per_frame" not in ds or "val_all" not in ds:
+            raise UnsupportedPipeline("color_transform needs the dataset's total_images_per_frame / val_all")
+        color_views = int(ds["total_images_per_frame"])
+        tf, sf = _get(ctrans, "out_transform_field", "color_transform_global"), _get(ctrans, "out_shift_field", "color_shift_global")
+        if tf != "color_transform_global" or sf != "color_shift_global":
+            raise UnsupportedPipeline("color_transform with renamed output fields")
+        if bool(ds["val_all"]) and not glob[0] and tf in fields:
+            if sf not in fields:
+                raise UnsupportedPipeline("color_transform_global reaches the colour net without color_shift_global")
+            if color_views < 1:
+                raise UnsupportedPipeline("color_transform without camera views")
+            c.n_color_views = color_views
+            c.act_ctransform = resolve_activation(_get(ctrans, "transform_activation", "identity"), cur_iter)
+            c.act_ctshift = resolve_activation(_get(ctrans, "shift_activation", "identity"), cur_iter)
+            c.c_in = 8  # the camera id is rays[..., -2] (point.py:598)
     c.use_color_scale_shift = int("color_scale" in offs and "color_scale" in fields and "color_shift" in offs and "color_shift" in fields)
     if ("color_scale" in offs and "color_scale" in fields) != ("color_shift" in offs and "color_shift" in fields):
         raise UnsupportedPipeline("color_scale and color_shift must come together")
@@ -507,4 +607,5 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     c.density_shift = float(_get(net, "density_shift", -10.0))
     c.clamp_output = 1
     return Signature(cfg=c, model_cfg=m, dataset=ds, head_names=head_names, head_channels=head_channels,
-                     mlp_layer_shapes=shapes, dynamic=dynamic, in_perm=in_perm)
+                     mlp_layer_shapes=shapes, dynamic=dynamic, in_perm=in_perm, color_views=color_views,
+                     color_embedding_index=ctrans_index)

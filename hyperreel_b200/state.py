@@ -45,10 +45,24 @@ class _Prediction(nn.Module):
         self.net = _SampleNet(shapes)
 
 
-class _Embedding(nn.Module):
-    def __init__(self, shapes):
+class _ColorTransform(nn.Module):
+    """Storage twin of ColorTransformEmbedding (nlf/embedding/point.py:558-592): one 3x3 transform + shift per camera, zeros."""
+
+    def __init__(self, views: int):
         super().__init__()
-        self.embeddings = nn.ModuleList([_Prediction(shapes)])
+        self.color_embedding = nn.Parameter(torch.zeros(views, 12))
+
+
+class _Embedding(nn.Module):
+    """`embeddings` mirrors RayPointEmbedding's ModuleList (nlf/embedding/embedding.py:80-96): one entry per YAML key, in
+    order; entries without parameters are empty modules (they add no state_dict keys)."""
+
+    def __init__(self, shapes, color_views: int = 0, color_index: int = -1):
+        super().__init__()
+        mods = [_Prediction(shapes)]
+        if color_views > 0 and color_index > 0:
+            mods += [nn.Module() for _ in range(color_index - 1)] + [_ColorTransform(color_views)]
+        self.embeddings = nn.ModuleList(mods)
 
 
 class _Tensorf(nn.Module):
@@ -153,7 +167,9 @@ def seeded_state_dict(sig: Signature, grid: Optional[Sequence[int]] = None, seed
     grid = list(grid) if grid is not None else default_grid(sig)
     with torch.random.fork_rng(devices=[]):
         torch.manual_seed(seed)
-        emb = _Embedding(sig.mlp_layer_shapes)
+        emb = _Embedding(sig.mlp_layer_shapes, sig.color_views, sig.color_embedding_index)
+        if sig.color_views > 0:  # the reference initialises the table with zeros (identity transform): give the tests something to see
+            emb.embeddings[sig.color_embedding_index].color_embedding.data.normal_(0.0, 0.5)
         col = _Color(sig, grid)
     sd = {}
     for k, v in emb.state_dict().items():

@@ -25,11 +25,11 @@
 extern "C" {
 #endif
 
-#define HR_ABI_VERSION 9
+#define HR_ABI_VERSION 10
 
 #define HR_MAX_GROUPS 4   /* ray-parameterisation groups feeding the sample net (ray.py:235-263) */
 #define HR_MAX_LAYERS 10  /* Linear layers of the sample net (mlp.py:127-154) */
-#define HR_MAX_SAMPLES 64 /* z_channels S (per-ray sample primitives) */
+#define HR_MAX_SAMPLES 256 /* z_channels S (per-ray sample primitives) */
 #define HR_MAX_PEERS 8    /* destination buffers of hr_render_scatter (GPUs of one NVSwitch domain) */
 
 /* Activation y = f(x*inner_fac + shift) * outer_fac  (nlf/activations.py:53-69,121-137,163-178).
@@ -55,7 +55,9 @@ typedef struct hr_encode_group {
 } hr_encode_group;
 
 enum { HR_ISECT_Z_PLANE = 0, HR_ISECT_SPHERE = 1, HR_ISECT_CYLINDER = 2, HR_ISECT_SPHERE_NEW = 3,
-       HR_ISECT_DISTANCE = 4 };  /* z.py:16-97, primitive.py:366-438, :181-250, :440-546, :126-180 (euclidean_distance_unified) */
+       HR_ISECT_DISTANCE = 4,  /* z.py:16-97, primitive.py:366-438, :181-250, :440-546, :126-180 (euclidean_distance_unified) */
+       HR_ISECT_VOXEL = 5,     /* voxel_grid: axis-aligned planes, sample s = plane s/3 of axis s%3 (voxel.py:19-112)        */
+       HR_ISECT_PLANE = 6 };   /* deformable_voxel_grid: predicted plane normals + offsets (voxel.py:115-214)                */
 enum { HR_CONTRACT_NONE = 0, HR_CONTRACT_MIPNERF = 1, HR_CONTRACT_AFFINE = 2 };  /* AFFINE: bbox / z_depth (contract.py:65-110) */
 enum { HR_SHADE_SH = 0, HR_SHADE_RGB = 1 };
 enum { HR_DENSE_RELU = 0, HR_DENSE_SOFTPLUS = 1, HR_DENSE_RELU_ABS = 2 };
@@ -147,6 +149,21 @@ typedef struct hr_config {
    * origin = z[0:3] * sphere_origin_scale, resize = z[3:6] * sphere_resize_scale + sphere_resize_initial           */
   float sphere_resize_scale;
   float sphere_resize_initial[3];
+
+  /* --- ABI 10 additions --- */
+  /* HR_ISECT_VOXEL / HR_ISECT_PLANE: `samples` holds one linspace per axis interleaved (sample s = plane s / isect_axes of
+   * axis s % isect_axes); z_scale3 = spacing per axis (voxel.py:58-63; HR_ISECT_PLANE and the other primitives: z_scale x3) */
+  int32_t isect_axes;       /* 3 (voxel_grid), number of start normals (deformable_voxel_grid), 1 otherwise              */
+  float z_scale3[3];
+  int32_t isect_outward;    /* voxel_grid outward_facing: z *= sign(d_axis) (voxel.py:80-83)                            */
+  int32_t isect_max_axis;   /* voxel_grid max_axis: drop the planes of the non-dominant axes (voxel.py:100-110)          */
+  float plane_normal[9];    /* deformable_voxel_grid start_normal rows (voxel.py:120-128)                                */
+  float plane_normal_scale; /* normal_scale_factor (voxel.py:129)                                                        */
+  /* ColorTransformEmbedding (point.py:558-612) + transform_color_one (utils/tensorf_utils.py:308-331): the composited pixel
+   * becomes rgb + M rgb + shift with (M, shift) = row round(rays[:, -2]) of hr_params.color_embedding [n_color_views, 12];
+   * 0 = off (no such embedding, or the dataset does not validate on every camera) */
+  int32_t n_color_views;
+  hr_act act_ctransform, act_ctshift;
 } hr_config;
 
 /* Parameters in the reference's own state_dict layout, fp32, contiguous.
@@ -167,6 +184,7 @@ typedef struct hr_params {
   const float* app_second[3];
   int32_t second_len[3];                 /* L_i                                          */
   const float* basis_mat;                /* basis_mat.weight [app_dim, sum(n_app)]       */
+  const float* color_embedding;          /* embeddings.{i}.color_embedding [n_color_views, 12] (NULL when n_color_views == 0) */
 } hr_params;
 
 typedef struct hr_handle hr_handle;

@@ -167,6 +167,10 @@ def make_system(dataset: dict):
         far=dataset.get("far", 1.0),
         depth_range=dataset.get("depth_range", [dataset.get("near", 0.0), dataset.get("far", 1.0)]),
     )
+    for k in ("bbox_min", "bbox_max", "total_images_per_frame", "val_all"):  # voxel.py:27-29, point.py:574-575
+        if k in dataset:
+            v = dataset[k]
+            setattr(ds, k, torch.tensor(v) if k.startswith("bbox") else v)
     cfg = to_attr({"dataset": {"collection": dataset.get("collection", "synthetic"),
                                "name": dataset.get("name", "synthetic")}})
     return SimpleNamespace(dm=SimpleNamespace(train_dataset=ds), cfg=cfg)

@@ -164,7 +164,8 @@ def test_shipped_model_yamls_that_lower_to_the_fused_path():
     """Coverage ledger over the reference's 51 shipped model YAMLs: these must lower (DESIGN.md section 7 lists why the
     rest are rejected)."""
     import glob
-    ds = {"num_keyframes": 12, "num_frames": 50, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y"}
+    ds = {"num_keyframes": 12, "num_frames": 50, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y",
+          "bbox_min": [-1.5, -1.25, -1.0], "bbox_max": [1.5, 1.25, 1.0], "total_images_per_frame": 5, "val_all": True}
     ok = set()
     for f in sorted(glob.glob("/root/reference/conf/experiment/model/*.yaml")):
         try:
@@ -181,8 +182,11 @@ def test_shipped_model_yamls_that_lower_to_the_fused_path():
         "technicolor_z_plane_world", "immersive_sphere", "immersive_sphere_test", "immersive_cylinder", "immersive_cylinder_pe",
         "bom_cylinder", "catacaustics_z_plane", "catacaustics_cylinder", "shiny_z_plane", "stanford_llff_z_plane", "immersive_sphere_new", "bom_sphere",
         "catacaustics_distance",
+        # round 2: voxel grids (axis-aligned and deformable), 96 / 128 / 256 samples per ray, the per-camera colour transform
+        "catacaustics_voxel", "donerf_voxel", "shiny_z_deformable", "neural_3d_z_plane_static", "technicolor_z_plane_no_sample",
+        "immersive_z_plane",
     }
-    assert len(ok) >= 35
+    assert len(ok) >= 41
     assert expected <= ok, sorted(expected - ok)
 
 

@@ -95,7 +95,8 @@ def test_oracle_matches_reference_on_every_shipped_yaml_that_lowers():
     ref_shim.install()
     from nlf.rendering import render_chunked
 
-    ds = {"num_keyframes": 12, "num_frames": 50, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y"}
+    ds = {"num_keyframes": 12, "num_frames": 50, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y",
+          "bbox_min": [-1.5, -1.25, -1.0], "bbox_max": [1.5, 1.25, 1.0], "total_images_per_frame": 5, "val_all": True}
     checked, nonzero = 0, 0
     for f in sorted(glob.glob(os.path.join(ref_shim.REFERENCE_ROOT, "conf/experiment/model/*.yaml"))):
         cfg = hb.load_model_yaml(f)
@@ -119,13 +120,15 @@ def test_oracle_matches_reference_on_every_shipped_yaml_that_lowers():
         assert float((a.reshape(b.shape) - b).abs().max()) <= 2e-6, os.path.basename(f)
         checked += 1
         nonzero += int(float(b.abs().max()) > 0)
-    assert checked >= 35 and nonzero >= 30
+    assert checked >= 41 and nonzero >= 36
 
 
-def test_three_shipped_yamls_do_not_run_in_the_reference_itself():
-    """Coverage ledger honesty: catacaustics_sphere / refnerf_sphere (8 z channels into the 4-channel `sphere` primitive) and
-    shiny_z_tensorf (`z` is not a registered intersect type) fail inside the unmodified reference, so no implementation can be
-    held to them; they are excluded from the denominator in DESIGN.md section 7."""
+def test_seven_shipped_yamls_do_not_run_in_the_reference_itself():
+    """Coverage ledger honesty: catacaustics_sphere / refnerf_sphere (8 z channels into the 4-channel `sphere` primitive),
+    shiny_z_tensorf (`z` is not a registered intersect type), donerf_z / shiny_z_depth (`epipolar` is not a registered embedding
+    type), blender_voxel (its ray_prediction has no `params`) and shiny_z_tensorf_cascaded (a string threshold compared with a
+    tensor) fail inside the unmodified reference, so no implementation can be held to them; together with the empty
+    bom_z_plane.yaml they are excluded from the denominator in DESIGN.md section 7."""
     import hyperreel_b200 as hb
     from hyperreel_b200.config import to_plain
 
@@ -133,12 +136,13 @@ def test_three_shipped_yamls_do_not_run_in_the_reference_itself():
     from nlf.rendering import render_chunked
 
     ds = {"num_keyframes": 12, "num_frames": 50, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y"}
-    for name in ("catacaustics_sphere", "refnerf_sphere", "shiny_z_tensorf"):
+    for name in ("catacaustics_sphere", "refnerf_sphere", "shiny_z_tensorf", "donerf_z", "shiny_z_depth", "blender_voxel",
+                 "shiny_z_tensorf_cascaded"):
         cfg = hb.load_model_yaml(f"{ref_shim.REFERENCE_ROOT}/conf/experiment/model/{name}.yaml")
         cfg.color.net.N_voxel_init = cfg.color.net.N_voxel_final = 16 ** 3
         rays = torch.randn(8, 6) * 0.3
         rays[:, 3:6] = torch.nn.functional.normalize(torch.randn(8, 3), dim=-1)
-        with pytest.raises((RuntimeError, KeyError)):
+        with pytest.raises((RuntimeError, KeyError, AttributeError, TypeError)):
             ref = ref_shim.build_reference(to_plain(cfg), ds)
             with torch.no_grad():
                 render_chunked(rays, ref, {}, 8)
