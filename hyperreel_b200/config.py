@@ -47,12 +47,36 @@ def to_plain(o: Any) -> Any:
     return o
 
 
+def _yaml_loader():
+    """PyYAML's SafeLoader with the float resolver OmegaConf installs (omegaconf/_utils.py:get_yaml_loader): YAML 1.1 reads
+    ``1e-4`` (no dot) as a string, Hydra/OmegaConf -- what the reference is launched through -- as a float
+    (``rm_weight_mask_thre: 1e-4`` in shiny_z_tensorf_cascaded.yaml is compared with a tensor, tensorf_no_sample.py:201)."""
+    import re
+
+    import yaml
+
+    class Loader(yaml.SafeLoader):
+        pass
+
+    Loader.add_implicit_resolver(
+        "tag:yaml.org,2002:float",
+        re.compile(r"""^(?:
+         [-+]?(?:[0-9][0-9_]*)\.[0-9_]*(?:[eE][-+]?[0-9]+)?
+        |[-+]?(?:[0-9][0-9_]*)(?:[eE][-+]?[0-9]+)
+        |\.[0-9_]+(?:[eE][-+][0-9]+)?
+        |[-+]?[0-9][0-9_]*(?::[0-5]?[0-9])+\.[0-9_]*
+        |[-+]?\.(?:inf|Inf|INF)
+        |\.(?:nan|NaN|NAN))$""", re.X),
+        list("-+0123456789."))
+    return Loader
+
+
 def load_model_yaml(path: str) -> Cfg:
     """Read one ``conf/experiment/model/<name>.yaml`` of a reference checkout (unforked, read-only)."""
     import yaml
 
     with open(path) as f:
-        return to_cfg(yaml.safe_load(f))
+        return to_cfg(yaml.load(f, Loader=_yaml_loader()))
 
 
 def epochs_to_iters(cfg: Any, iters_per_epoch: int) -> Any:

@@ -13,6 +13,7 @@
 
 #include "hr_common.cuh"
 #include "hr_encode.cuh"
+#include "hr_geom.cuh"
 #include "hr_mlp.cuh"
 #include "hyperreel_b200.h"
 
@@ -167,6 +168,62 @@ __global__ void encode_rays_kernel(const __grid_constant__ hr_config cfg, const 
     hr::encode_ray(cfg, rays + i * cfg.c_in, enc + i * cfg.mlp_in, 1);
 }
 
+// First stage of a cascaded pipeline (PointPredictionEmbedding, nlf/embedding/point.py:142-160): one warp per ray,
+// lane = first-stage sample.  heads0 [n][c*S0+s] are the ray net's outputs (null: `zero` net); the S0 z-planes are
+// intersected, masked and sorted like any other (Intersect.forward, base.py:142-226; IntersectZPlane, z.py:77-97), and every
+// point o + t d becomes one 8-float input row of the point net (channel k holds cfg.pt_src[k]).
+__global__ void cascade_points_kernel(const __grid_constant__ hr_config cfg, const float* __restrict__ rays,
+                                      const float* __restrict__ heads0, float* __restrict__ rows, long long n) {
+  const int lane = threadIdx.x & 31;
+  const int S0 = cfg.pre_samples;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int out0 = S0 * cfg.pre_head_stride;
+  for (long long ray = warp0; ray < n; ray += nwarps) {
+    const float* r = rays + ray * cfg.c_in;
+    const float ox = __ldg(r + 0), oy = __ldg(r + 1), oz = __ldg(r + 2);
+    const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
+    const float time = __ldg(r + cfg.c_in - 1);
+    const bool act = lane < S0;
+    const int s = act ? lane : 0;
+    const float zraw = heads0 ? __ldg(heads0 + ray * out0 + cfg.pre_off_z * S0 + s) : 0.0f;
+    const float sraw = (heads0 && cfg.pre_off_sigma >= 0) ? __ldg(heads0 + ray * out0 + cfg.pre_off_sigma * S0 + s) : 0.0f;
+    const float sg = cfg.pre_use_sigma ? hr::apply_act(cfg.pre_act_sigma, sraw) : 0.0f;
+    const float zr = __fmul_rn(hr::apply_act(cfg.pre_isect_act, hr::apply_act(cfg.pre_act_z, zraw)), __fsub_rn(1.0f, sg));
+    const float z = __fadd_rn(__fmul_rn(zr, cfg.pre_z_scale), cfg.pre_samples_tab[s]);
+    const float dzg = (fabsf(dz) < 1e-5f) ? 1e12f : dz;  // intersect_utils.py:135-142
+    float t = __fdiv_rn(__fsub_rn(z, oz), dzg);
+    if ((t <= cfg.pre_near) || (t >= cfg.pre_far)) t = 0.0f;
+    float key[1] = {act ? t : __int_as_float(0x7f800000)};
+    if (cfg.pre_sort) hr::sort_keys<1>(key, lane);
+    t = key[0];
+    if (!act) continue;
+    const float px = __fadd_rn(ox, __fmul_rn(dx, t)), py = __fadd_rn(oy, __fmul_rn(dy, t)), pz = __fadd_rn(oz, __fmul_rn(dz, t));
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float x = 0.0f;
+      switch (cfg.pt_src[k]) {
+        case HR_PT_POINT_X: x = px; break;
+        case HR_PT_POINT_Y: x = py; break;
+        case HR_PT_POINT_Z: x = pz; break;
+        case HR_PT_VIEW_X: x = dx; break;
+        case HR_PT_VIEW_Y: x = dy; break;
+        case HR_PT_VIEW_Z: x = dz; break;
+        case HR_PT_ORIGIN_X: x = ox; break;
+        case HR_PT_ORIGIN_Y: x = oy; break;
+        case HR_PT_ORIGIN_Z: x = oz; break;
+        case HR_PT_TIME: x = time; break;
+        default: break;
+      }
+      v[k] = x;
+    }
+    float4* dst = reinterpret_cast<float4*>(rows + (ray * S0 + lane) * 8);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 // gradient table [H][W][C] (channel-last, the kernels' layout) -> reference layout [C][H][W]
 __global__ void unpack_channel_last(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W) {
   long long total = (long long)C * H * W;
@@ -266,6 +323,24 @@ int validate(const hr_config& c) {
     return fail("voxel_grid needs 1 z channel and a multiple of 3 samples");
   if (c.isect_type == HR_ISECT_PLANE && (c.n_z != 4 || c.isect_axes < 1 || c.isect_axes > 3 || c.n_samples % c.isect_axes != 0))
     return fail("deformable_voxel_grid needs 4 z channels and 1-3 axes dividing the sample count");
+  if (c.cascade) {
+    if (c.pre_samples < 1 || c.pre_samples > 32 || c.n_samples % c.pre_samples != 0) return fail("cascade: bad pre_samples %d", c.pre_samples);
+    if (c.mlp_mode == HR_MLP_ZERO) return fail("cascade: the point net cannot be a zero net");
+    if (c.pre_mlp_mode != HR_MLP_ZERO && c.pre_mlp_mode != c.mlp_mode) return fail("cascade: pre_mlp_mode must be zero or mlp_mode");
+    if (c.pre_head_stride < 1 || c.pre_off_z < 0 || c.pre_off_z >= c.pre_head_stride || c.pre_off_sigma >= c.pre_head_stride)
+      return fail("cascade: bad first-stage head layout");
+    if (c.pre_mlp_mode != HR_MLP_ZERO) {
+      if (c.pre_n_groups < 1 || c.pre_n_groups > HR_MAX_GROUPS) return fail("cascade: unsupported pre_n_groups %d", c.pre_n_groups);
+      if (c.pre_mlp_layers < 2 || c.pre_mlp_layers > HR_MAX_LAYERS) return fail("cascade: unsupported pre_mlp_layers %d", c.pre_mlp_layers);
+      if (c.pre_mlp_width != 128 && c.pre_mlp_width != 256) return fail("cascade: unsupported pre_mlp_width %d", c.pre_mlp_width);
+      if (c.pre_mlp_in < 1 || c.pre_mlp_in > 64) return fail("cascade: unsupported pre_mlp_in %d", c.pre_mlp_in);
+      if (c.pre_mlp_skip != -1 && (c.pre_mlp_skip < 1 || c.pre_mlp_skip > c.pre_mlp_layers - 2)) return fail("cascade: bad pre_mlp_skip");
+      if ((c.pre_samples * c.pre_head_stride) % 4 != 0) return fail("cascade: first-stage output width must be a multiple of 4");
+    }
+    if ((c.mlp_out / c.pre_samples) % 4 != 0) return fail("cascade: the point net's output width must be a multiple of 4");
+    for (int g = 0; g < c.n_groups; ++g)
+      if (c.groups[g].start < 0 || c.groups[g].end > 8) return fail("cascade: point-net param group outside the 8-channel row");
+  }
   if (c.n_color_views < 0) return fail("bad n_color_views");
   if (c.n_color_views > 0 && c.c_in != 8) return fail("colour transform needs 8-channel rays (camera id = rays[:, -2])");
   if (c.n_color_views > 0 && c.off_cscale_global >= 0) return fail("colour transform and global colour heads are exclusive");
@@ -338,6 +413,29 @@ int hr_create(const hr_config* cfg, int device, hr_handle** out) {
   memset(&h->tabs, 0, sizeof(h->tabs));
   memset(&h->simt, 0, sizeof(h->simt));
   memset(&h->tc, 0, sizeof(h->tc));
+  memset(&h->simt_pre, 0, sizeof(h->simt_pre));
+  memset(&h->tc_pre, 0, sizeof(h->tc_pre));
+  h->cfg_net = h->cfg;
+  h->cfg_pre = h->cfg;
+  if (h->cfg.cascade) {
+    const hr_config& c = h->cfg;
+    // the point net: one 8-float row per first-stage point in, n_samples / pre_samples samples out, columns in the
+    // reference's order (n_samples = 1 makes the packers' channel-major permutation the identity)
+    hr_config& n = h->cfg_net;
+    n.c_in = 8;
+    n.mlp_out = c.mlp_out / c.pre_samples;
+    n.n_samples = 1;
+    n.head_stride = n.mlp_out;
+    // the first-stage ray net
+    hr_config& q = h->cfg_pre;
+    q.n_groups = c.pre_n_groups;
+    for (int g = 0; g < HR_MAX_GROUPS; ++g) q.groups[g] = c.pre_groups[g];
+    q.mlp_in = c.pre_mlp_in; q.mlp_width = c.pre_mlp_width; q.mlp_layers = c.pre_mlp_layers; q.mlp_skip = c.pre_mlp_skip;
+    q.mlp_mode = c.pre_mlp_mode;
+    q.n_samples = c.pre_samples;
+    q.head_stride = c.pre_head_stride;
+    q.mlp_out = c.pre_samples * c.pre_head_stride;
+  }
   *out = h;
   return 0;
 }
@@ -358,40 +456,48 @@ int hr_upload(hr_handle* h, const hr_params* p, void* stream) {
   std::vector<void*> temps;
   int rc = 0;
 
-  // ---- sample net ----
-  const int L = c.mlp_layers, W = c.mlp_width;
-  const int in_pad = (c.mlp_in + 15) / 16 * 16;
-  h->simt.in_pad = in_pad;
-  h->simt.n_layers = L;
-  h->simt.skip = c.mlp_skip;
-  const float* w_dev[HR_MAX_LAYERS] = {nullptr};
-  const float* b_dev[HR_MAX_LAYERS] = {nullptr};
-  for (int l = 0; l < L && !rc && c.mlp_mode != HR_MLP_ZERO; ++l) {
-    if (!p->mlp_weight[l] || !p->mlp_bias[l]) { rc = fail("hr_upload: mlp layer %d missing", l); break; }
-    const bool first = (l == 0), last = (l == L - 1), skip = (l == c.mlp_skip);
-    const int in_src = first ? c.mlp_in : (skip ? c.mlp_in + W : W);
-    const int out_ch = last ? c.mlp_out : W;
-    const int Kp = first ? in_pad : (skip ? in_pad + W : W);
-    const int Np = last ? (c.mlp_out + W - 1) / W * W : W;
-    rc = stage_in(p->mlp_weight[l], (size_t)out_ch * in_src, p->on_device, st, temps, &w_dev[l]);
-    if (rc) break;
-    rc = stage_in(p->mlp_bias[l], (size_t)out_ch, p->on_device, st, temps, &b_dev[l]);
-    if (rc) break;
-    float *Wt = nullptr, *bias = nullptr;
-    if ((rc = dev_alloc(h, (void**)&Wt, (size_t)Kp * Np * sizeof(float)))) break;
-    if ((rc = dev_alloc(h, (void**)&bias, (size_t)Np * sizeof(float)))) break;
-    pack_simt_layer<<<grid_for((long long)Kp * Np + Np), 256, 0, st>>>(
-        w_dev[l], b_dev[l], Wt, bias, Kp, Np, out_ch, in_src, c.mlp_in, in_pad, (first || skip) ? 1 : 0, skip ? 1 : 0, W,
-        last ? c.n_samples : 0, c.head_stride);
-    h->simt.Wt[l] = Wt;
-    h->simt.bias[l] = bias;
-    h->simt.Kp[l] = Kp;
-    h->simt.Np[l] = Np;
-  }
-  if (!rc && c.mlp_mode == HR_MLP_BF16X3_TC) {
-    rc = hr::pack_mlp_tc2(h, w_dev, b_dev, st);
-    if (!rc) h->tc_ready = true;
-  }
+  // ---- sample net(s) ----
+  auto pack_net = [&](const hr_config& nc, const float* const* wsrc, const float* const* bsrc, hr::MlpSimtPack& simt,
+                      hr::MlpTcPack& tc, bool& tc_ready, size_t& tc_bytes, int& tc_bias) -> int {
+    const int L = nc.mlp_layers, W = nc.mlp_width;
+    const int in_pad = (nc.mlp_in + 15) / 16 * 16;
+    simt.in_pad = in_pad;
+    simt.n_layers = L;
+    simt.skip = nc.mlp_skip;
+    tc_ready = false;
+    const float* w_dev[HR_MAX_LAYERS] = {nullptr};
+    const float* b_dev[HR_MAX_LAYERS] = {nullptr};
+    int r = 0;
+    for (int l = 0; l < L && !r && nc.mlp_mode != HR_MLP_ZERO; ++l) {
+      if (!wsrc[l] || !bsrc[l]) return fail("hr_upload: mlp layer %d missing", l);
+      const bool first = (l == 0), last = (l == L - 1), skip = (l == nc.mlp_skip);
+      const int in_src = first ? nc.mlp_in : (skip ? nc.mlp_in + W : W);
+      const int out_ch = last ? nc.mlp_out : W;
+      const int Kp = first ? in_pad : (skip ? in_pad + W : W);
+      const int Np = last ? (nc.mlp_out + W - 1) / W * W : W;
+      if ((r = stage_in(wsrc[l], (size_t)out_ch * in_src, p->on_device, st, temps, &w_dev[l]))) break;
+      if ((r = stage_in(bsrc[l], (size_t)out_ch, p->on_device, st, temps, &b_dev[l]))) break;
+      float *Wt = nullptr, *bias = nullptr;
+      if ((r = dev_alloc(h, (void**)&Wt, (size_t)Kp * Np * sizeof(float)))) break;
+      if ((r = dev_alloc(h, (void**)&bias, (size_t)Np * sizeof(float)))) break;
+      pack_simt_layer<<<grid_for((long long)Kp * Np + Np), 256, 0, st>>>(
+          w_dev[l], b_dev[l], Wt, bias, Kp, Np, out_ch, in_src, nc.mlp_in, in_pad, (first || skip) ? 1 : 0, skip ? 1 : 0, W,
+          last ? nc.n_samples : 0, nc.head_stride);
+      simt.Wt[l] = Wt;
+      simt.bias[l] = bias;
+      simt.Kp[l] = Kp;
+      simt.Np[l] = Np;
+    }
+    if (!r && nc.mlp_mode == HR_MLP_BF16X3_TC) {
+      r = hr::pack_mlp_tc2(h, nc, tc, tc_bytes, tc_bias, w_dev, b_dev, st);
+      if (!r) tc_ready = true;
+    }
+    return r;
+  };
+  rc = pack_net(h->cfg_net, p->mlp_weight, p->mlp_bias, h->simt, h->tc, h->tc_ready, h->tc_alloc_bytes, h->tc_alloc_bias);
+  if (!rc && c.cascade)
+    rc = pack_net(h->cfg_pre, p->pre_mlp_weight, p->pre_mlp_bias, h->simt_pre, h->tc_pre, h->tc_pre_ready, h->tc_pre_alloc_bytes,
+                  h->tc_pre_alloc_bias);
 
   // ---- VM tables, channel-last ----
   auto pack_tab = [&](const float* src, int C, int H, int Wd, const float** out) -> int {
@@ -520,10 +626,22 @@ static int64_t sub_batch_rays(const hr_handle* h) {
   return (int64_t)h->num_sms * 128 * 16;
 }
 
+// scratch of the first stage of a cascaded pipeline for n rays, placed after the heads: first-stage heads [n][S0*stride0],
+// point rows [n*S0][8], point-net output [n][mlp_out] (reference order, before the channel-major permutation)
+static int64_t cascade_bytes(const hr_handle* h, int64_t n_rays) {
+  const hr_config& c = h->cfg;
+  if (!c.cascade) return 0;
+  const int64_t per_ray = (int64_t)c.pre_samples * c.pre_head_stride + (int64_t)c.pre_samples * 8 + c.mlp_out;
+  return (n_rays * per_ray * (int64_t)sizeof(float) + 255) / 256 * 256;
+}
+
+// workspace of one render call over n rays that is not split further
+static int64_t ws_bytes_for(const hr_handle* h, int64_t n_rays) { return heads_bytes(h, n_rays) + cascade_bytes(h, n_rays); }
+
 int64_t hr_workspace_bytes(const hr_handle* h, int64_t n_rays) {
   if (!h || n_rays < 0) return -1;
   const int64_t sub = sub_batch_rays(h);
-  return heads_bytes(h, (h->sub_rays < 0 || n_rays < sub) ? n_rays : sub);
+  return ws_bytes_for(h, (h->sub_rays < 0 || n_rays < sub) ? n_rays : sub);
 }
 
 int64_t hr_train_workspace_bytes(const hr_handle* h, int64_t n_rays) {
@@ -544,23 +662,50 @@ static void drop_host_graph(hr_handle* h) {
   h->pipe.g_rays = nullptr; h->pipe.g_rgb = nullptr; h->pipe.g_n = 0; h->pipe.g_chunk = 0;
 }
 
-// rays [n, c_in] -> heads scratch [n, mlp_out] (channel-major per ray)
-static int launch_sample_net(hr_handle* h, const float* rays, int64_t n, float* heads, cudaStream_t st) {
-  const hr_config& c = h->cfg;
+// one net (ray net or point net) over `rows` input rows -> out [rows][nc.mlp_out]
+static int launch_net(hr_handle* h, const hr_config& nc, const hr::MlpSimtPack& simt, const hr::MlpTcPack& tc, bool tc_ready,
+                      const float* in, int64_t rows, float* out, cudaStream_t st) {
   cudaError_t e;
-  if (c.mlp_mode == HR_MLP_ZERO) {  // ZeroMLP (nlf/nets/mlp.py:29-30): x.new_zeros(N, out_channels)
-    e = cudaMemsetAsync(heads, 0, (size_t)n * c.mlp_out * sizeof(float), st);
+  if (nc.mlp_mode == HR_MLP_ZERO) {  // ZeroMLP (nlf/nets/mlp.py:29-30): x.new_zeros(N, out_channels)
+    e = cudaMemsetAsync(out, 0, (size_t)rows * nc.mlp_out * sizeof(float), st);
     if (e != cudaSuccess) return fail("heads memset failed: %s", cudaGetErrorString(e));
     return 0;
   }
-  if (c.mlp_mode == HR_MLP_BF16X3_TC) {
-    if (!h->tc_ready) return fail("hr_render: tensor-core pack missing");
-    e = hr::launch_mlp_tc2(c, h->tc, h->tma_encode, rays, heads, n, h->num_sms, st);
+  if (nc.mlp_mode == HR_MLP_BF16X3_TC) {
+    if (!tc_ready) return fail("hr_render: tensor-core pack missing");
+    e = hr::launch_mlp_tc2(nc, tc, h->tma_encode, in, out, rows, h->num_sms, st);
   } else {
-    e = hr::launch_mlp_simt(c, h->simt, rays, heads, n, h->num_sms, st);
+    e = hr::launch_mlp_simt(nc, simt, in, out, rows, h->num_sms, st);
   }
   if (e != cudaSuccess) return fail("sample-net launch failed: %s", cudaGetErrorString(e));
   h->launches += 1;
+  return 0;
+}
+
+// rays [n, c_in] -> heads scratch [n, mlp_out] (channel-major per ray).  `scratch` (cascade_bytes(h, n), only read for a
+// cascaded pipeline) holds the first stage's intermediates.
+static int launch_sample_net(hr_handle* h, const float* rays, int64_t n, float* heads, cudaStream_t st, void* scratch = nullptr) {
+  const hr_config& c = h->cfg;
+  if (!c.cascade) return launch_net(h, h->cfg_net, h->simt, h->tc, h->tc_ready, rays, n, heads, st);
+  if (!scratch) return fail("hr_render: cascade scratch missing");
+  // PointPredictionEmbedding (nlf/embedding/point.py:142-206): ray net -> S0 z-planes -> one point-net row per point
+  float* heads0 = (float*)scratch;                                                   // [n][S0*stride0] channel-major
+  float* rows = heads0 + n * (int64_t)c.pre_samples * c.pre_head_stride;             // [n*S0][8]
+  float* out = rows + n * (int64_t)c.pre_samples * 8;                                // [n*S0][mlp_out/S0] = [n][S][stride]
+  const bool has_pre = c.pre_mlp_mode != HR_MLP_ZERO;
+  if (has_pre) {
+    int rc = launch_net(h, h->cfg_pre, h->simt_pre, h->tc_pre, h->tc_pre_ready, rays, n, heads0, st);
+    if (rc) return rc;
+  }
+  cascade_points_kernel<<<grid_for(n * 32), 256, 0, st>>>(c, rays, has_pre ? heads0 : nullptr, rows, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("cascade point kernel launch failed: %s", cudaGetErrorString(e));
+  int rc = launch_net(h, h->cfg_net, h->simt, h->tc, h->tc_ready, rows, n * c.pre_samples, out, st);
+  if (rc) return rc;
+  permute_heads<<<grid_for(n * (long long)c.mlp_out), 256, 0, st>>>(out, heads, n, c.n_samples, c.head_stride);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("heads permutation launch failed: %s", cudaGetErrorString(e));
+  h->launches += 2;
   return 0;
 }
 
@@ -593,7 +738,7 @@ static int render_impl(hr_handle* h, const float* rays, int64_t n, float* rgb, f
       CK(cudaEventCreate(&em.a)); CK(cudaEventCreate(&em.b)); CK(cudaEventCreate(&er.a)); CK(cudaEventCreate(&er.b));
       CK(cudaEventRecord(em.a, st));
     }
-    int rc0 = launch_sample_net(h, r, m, heads, st);
+    int rc0 = launch_sample_net(h, r, m, heads, st, (char*)workspace + heads_bytes(h, (n < sub) ? n : sub));
     if (rc0) return rc0;
     if (timing) { CK(cudaEventRecord(em.b, st)); CK(cudaEventRecord(er.a, st)); }
     hr::RgbDst d = scatter ? *scatter : one_dst(rgb);
@@ -728,7 +873,7 @@ int hr_render_frame_to8b_host(hr_handle* h, const hr_camera* cam, uint8_t* rgb8_
       P.d_rays[i] = P.d_rgb[i] = nullptr; P.d_ws[i] = nullptr;
       if (!P.streams[i]) CK(cudaStreamCreateWithFlags(&P.streams[i], cudaStreamNonBlocking));
     }
-    P.ws_bytes = heads_bytes(h, chunk);
+    P.ws_bytes = ws_bytes_for(h, chunk);
     for (int i = 0; i < 3; ++i) {
       CK(cudaMalloc((void**)&P.d_rays[i], (size_t)chunk * c.c_in * sizeof(float)));
       CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)chunk * 3 * sizeof(float)));
@@ -762,7 +907,8 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
   const int64_t wave = (int64_t)h->num_sms * 128;  // one full wave of 128-ray tiles of the tensor-core sample net
   // Default (chunk <= 0), tensor-core net, batches of a few waves: the "wave split" pipeline below.  Otherwise chunks of
   // `chunk` rays (default: whole waves for the tensor-core net, 32 768 rays for the CUDA-core net) on three streams.
-  const bool whole = chunk <= 0 && c.mlp_mode == HR_MLP_BF16X3_TC && n_rays <= 16 * wave;  // the batch stays whole on the device
+  // (a cascaded pipeline runs its nets on point rows: it takes the plain chunked pipeline)
+  const bool whole = chunk <= 0 && c.mlp_mode == HR_MLP_BF16X3_TC && n_rays <= 16 * wave && !c.cascade;  // the batch stays whole on the device
   const float* rays_dev_view = nullptr;
   if (whole && h->tc_ready && !h->timing) {
     cudaPointerAttributes pa;
@@ -785,7 +931,7 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
       P.d_rays[i] = P.d_rgb[i] = nullptr; P.d_ws[i] = nullptr;
       if (!P.streams[i]) CK(cudaStreamCreateWithFlags(&P.streams[i], cudaStreamNonBlocking));
     }
-    P.ws_bytes = heads_bytes(h, alloc);
+    P.ws_bytes = ws_bytes_for(h, alloc);
     for (int i = 0; i < 3; ++i) {
       CK(cudaMalloc((void**)&P.d_rays[i], (size_t)alloc * c.c_in * sizeof(float)));
       CK(cudaMalloc((void**)&P.d_rgb[i], (size_t)alloc * 3 * sizeof(float)));
@@ -927,6 +1073,7 @@ static int train_supported(const hr_config& c) {
   if (c.isect_type == HR_ISECT_VOXEL || c.isect_type == HR_ISECT_PLANE) return fail("backward: voxel-grid primitives are not supported yet");
   if (c.n_color_views > 0) return fail("backward: the per-camera colour transform is not supported yet");
   if (c.n_samples > 64) return fail("backward: more than 64 samples per ray are not supported yet");
+  if (c.cascade) return fail("backward: cascaded (point_prediction) pipelines are not supported yet");
   return 0;
 }
 
@@ -959,6 +1106,7 @@ static int ensure_grad_tables(hr_handle* h, cudaStream_t st) {
 
 int hr_encode_rays(hr_handle* h, const float* rays, int64_t n_rays, float* enc, void* stream) {
   if (!h || !rays || !enc) return fail("hr_encode_rays: null argument");
+  if (h->cfg.cascade) return fail("hr_encode_rays: a cascaded pipeline has two nets; its training path is not built");
   if (n_rays == 0) return 0;
   DeviceGuard guard(h->device);
   encode_rays_kernel<<<grid_for(n_rays), 256, 0, (cudaStream_t)stream>>>(h->cfg, rays, enc, n_rays);

@@ -38,11 +38,20 @@ struct hr_handle {
   std::vector<Slot> slots;   // device allocations of packed parameters, in hr_upload's request order
   size_t slot_cursor = 0;
   hr::RenderTabs tabs;
+  // the net behind the final heads (cfg_net == cfg, or the point net of a cascaded pipeline evaluated on 8-float point rows)
+  hr_config cfg_net;
   hr::MlpSimtPack simt;
   hr::MlpTcPack tc;
   bool tc_ready = false;
   size_t tc_alloc_bytes = 0;  // current allocation behind tc.wpack / tc.bias (reused while the layout is unchanged)
   int tc_alloc_bias = 0;
+  // cascaded pipelines only: the first-stage ray net (cfg.pre_*), same kernels
+  hr_config cfg_pre;
+  hr::MlpSimtPack simt_pre;
+  hr::MlpTcPack tc_pre;
+  bool tc_pre_ready = false;
+  size_t tc_pre_alloc_bytes = 0;
+  int tc_pre_alloc_bias = 0;
   void* tma_encode = nullptr; // cuTensorMapEncodeTiled, from cudaGetDriverEntryPoint
   // gradient tables of the backward pass (hr_render_backward), packed like the forward tables; allocated on first use
   float* g_sig_space[3] = {nullptr, nullptr, nullptr};

@@ -56,6 +56,8 @@ cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, void* tma_
 struct hr_handle;
 struct hr_params;
 namespace hr {
-int pack_mlp_tc2(hr_handle* h, const float* const* w_dev, const float* const* b_dev, cudaStream_t st);
+// packs the net `c` describes into `pk`; alloc_bytes / alloc_bias remember the allocation behind pk (reused while unchanged)
+int pack_mlp_tc2(hr_handle* h, const hr_config& c, MlpTcPack& pk, size_t& alloc_bytes, int& alloc_bias,
+                 const float* const* w_dev, const float* const* b_dev, cudaStream_t st);
 void free_mlp_tc2(hr_handle* h);
 }

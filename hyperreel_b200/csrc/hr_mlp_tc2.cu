@@ -478,9 +478,8 @@ mlp_tc2_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Ml
 }
 
 // Pass table + weight images (format: hr_tc_pack.cu).  Called by hr_upload with the handle's device current.
-int pack_mlp_tc2(hr_handle* h, const float* const* w_dev, const float* const* b_dev, cudaStream_t st) {
-  const hr_config& c = h->cfg;
-  MlpTcPack& pk = h->tc;
+int pack_mlp_tc2(hr_handle* h, const hr_config& c, MlpTcPack& pk, size_t& alloc_bytes, int& alloc_bias,
+                 const float* const* w_dev, const float* const* b_dev, cudaStream_t st) {
   const int W = c.mlp_width;
   if (W != 128 && W != 256) return hr_fail("tensor-core sample net: hidden width must be 128 or 256 (got %d)", W);
   if (c.mlp_in > 64) return hr_fail("tensor-core sample net: encoded input wider than 64 features (%d)", c.mlp_in);
@@ -517,18 +516,18 @@ int pack_mlp_tc2(hr_handle* h, const float* const* w_dev, const float* const* b_
   np_.n_passes = np;
   np_.bias_count = bias_off;
   np_.wpack_bytes = (long long)bytes;
-  if (h->tc_alloc_bytes != bytes || h->tc_alloc_bias != bias_off || !pk.wpack) {
+  if (alloc_bytes != bytes || alloc_bias != bias_off || !pk.wpack) {
     if (pk.wpack) cudaFree(const_cast<void*>(pk.wpack));
     if (pk.bias) cudaFree(const_cast<float*>(pk.bias));
     pk.wpack = nullptr; pk.bias = nullptr;
-    h->tc_alloc_bytes = 0; h->tc_alloc_bias = 0;
+    alloc_bytes = 0; alloc_bias = 0;
     void* wp = nullptr; float* bp = nullptr;
     cudaError_t e = cudaMalloc(&wp, bytes);
     if (e != cudaSuccess) return hr_fail("cudaMalloc(tc weights %zu): %s", bytes, cudaGetErrorString(e));
     e = cudaMalloc((void**)&bp, (size_t)bias_off * sizeof(float));
     if (e != cudaSuccess) { cudaFree(wp); return hr_fail("cudaMalloc(tc bias): %s", cudaGetErrorString(e)); }
     np_.wpack = wp; np_.bias = bp;
-    h->tc_alloc_bytes = bytes; h->tc_alloc_bias = bias_off;
+    alloc_bytes = bytes; alloc_bias = bias_off;
     // opt in to the 219 KB of dynamic shared memory once per (handle, device)
     e = cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
     if (e != cudaSuccess) return hr_fail("cudaFuncSetAttribute(mlp_tc2_kernel): %s", cudaGetErrorString(e));
@@ -565,6 +564,10 @@ void free_mlp_tc2(hr_handle* h) {
   if (h->tc.bias) cudaFree(const_cast<float*>(h->tc.bias));
   h->tc.wpack = nullptr; h->tc.bias = nullptr;
   h->tc_alloc_bytes = 0; h->tc_alloc_bias = 0;
+  if (h->tc_pre.wpack) cudaFree(const_cast<void*>(h->tc_pre.wpack));
+  if (h->tc_pre.bias) cudaFree(const_cast<float*>(h->tc_pre.bias));
+  h->tc_pre.wpack = nullptr; h->tc_pre.bias = nullptr;
+  h->tc_pre_alloc_bytes = 0; h->tc_pre_alloc_bias = 0;
 }
 
 cudaError_t launch_mlp_tc2(const hr_config& cfg, const MlpTcPack& pk, void* tma_encode, const float* rays, float* heads,

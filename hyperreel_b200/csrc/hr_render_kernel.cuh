@@ -109,7 +109,7 @@ __device__ __forceinline__ void group_products(const GroupTaps<C, DYN>& g, float
   for (int c = 0; c < 4; ++c) prod[c] = A[c] * B[c];
 }
 
-template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool EXTRA, int RPW>
+template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool EXTRA, int RPW, bool RARE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, SPL > 2 ? 1 : ((C1 + C2 == 0 || SPL == 1) ? 3 : 2))
 render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Derived dv,
               const __grid_constant__ RenderTabs tabs, const float* __restrict__ rays,
@@ -244,23 +244,6 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       }
     }
 
-    // ---- euclidean_distance_unified (primitive.py:126-180): samples are distances from the ray's point closest to the
-    // origin, base = d^ x (o x d^) (pluecker_pos, param.py:297-307); per ray: signed distance from o to that point
-    float base_distance = 0.0f;
-    if (cfg.isect_type == HR_ISECT_DISTANCE) {
-      const float nd = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
-      const float vx = __fdiv_rn(dx, nd), vy = __fdiv_rn(dy, nd), vz = __fdiv_rn(dz, nd);
-      const float mx = __fsub_rn(__fmul_rn(oy, vz), __fmul_rn(oz, vy));
-      const float my = __fsub_rn(__fmul_rn(oz, vx), __fmul_rn(ox, vz));
-      const float mz = __fsub_rn(__fmul_rn(ox, vy), __fmul_rn(oy, vx));
-      const float ex = __fsub_rn(__fsub_rn(__fmul_rn(vy, mz), __fmul_rn(vz, my)), ox);
-      const float ey = __fsub_rn(__fsub_rn(__fmul_rn(vz, mx), __fmul_rn(vx, mz)), oy);
-      const float ez = __fsub_rn(__fsub_rn(__fmul_rn(vx, my), __fmul_rn(vy, mx)), oz);
-      const float dotde = __fadd_rn(__fadd_rn(__fmul_rn(dx, ex), __fmul_rn(dy, ey)), __fmul_rn(dz, ez));
-      const float sgn = (dotde > 0.0f) ? 1.0f : ((dotde < 0.0f) ? -1.0f : 0.0f);
-      base_distance = __fmul_rn(sgn, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez))));
-    }
-
     // ---- lane = sample: intersection (base.py:155-203) ----
     float tkey[SPL], disp[SPL][3];
 #pragma unroll
@@ -280,105 +263,11 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         if (cfg.contract_samples) z = inv_contract_sample(cfg, dv, z);
         float dzg = (fabsf(dz) < 1e-5f) ? 1e12f : dz;  // intersect_utils.py:135-142
         t = __fdiv_rn(__fsub_rn(z, oz), dzg);
-      } else if (cfg.isect_type == HR_ISECT_VOXEL) {
-        // IntersectVoxelGrid (voxel.py:77-112) + intersect_voxel_grid (intersect_utils.py:152-179): sample s is plane s/3 of
-        // axis s%3; process_z_vals scales per axis (base.py:128-130)
-        const int ax = (act ? s : 0) % 3;
-        float zr = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, hz[j][0])), one_m);
-        float z = __fadd_rn(__fmul_rn(zr, cfg.z_scale3[ax]), samp);
-        if (cfg.contract_samples) z = inv_contract_sample(cfg, dv, z);
-        const float da = (ax == 0) ? dx : ((ax == 1) ? dy : dz);
-        const float oa = (ax == 0) ? ox : ((ax == 1) ? oy : oz);
-        if (cfg.isect_outward) z = __fmul_rn(z, (da > 0.0f) ? 1.0f : ((da < 0.0f) ? -1.0f : 0.0f));
-        const float dg = (fabsf(da) < 1e-5f) ? 1e12f : da;
-        t = __fdiv_rn(__fsub_rn(z, oa), dg);
-        if (cfg.isect_max_axis) {
-          const float dmax = fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz)));
-          if (fabsf(da) < __fsub_rn(dmax, 1e-8f)) t = 0.0f;
-        }
-      } else if (cfg.isect_type == HR_ISECT_PLANE) {
-        // IntersectDeformableVoxelGrid (voxel.py:178-214) + intersect_plane (intersect_utils.py:210-236): channels 0-2 bend
-        // the start normal of axis s % A, channel 3 is the plane offset
-        const int ax = (act ? s : 0) % cfg.isect_axes;
-        float zc[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) zc[c] = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, hz[j][c])), one_m);
-        float pd = __fadd_rn(__fmul_rn(zc[3], cfg.z_scale), samp);
-        if (cfg.contract_samples) pd = inv_contract_sample(cfg, dv, pd);
-        float nx = __fadd_rn(__fmul_rn(zc[0], cfg.plane_normal_scale), cfg.plane_normal[ax * 3 + 0]);
-        float ny = __fadd_rn(__fmul_rn(zc[1], cfg.plane_normal_scale), cfg.plane_normal[ax * 3 + 1]);
-        float nz = __fadd_rn(__fmul_rn(zc[2], cfg.plane_normal_scale), cfg.plane_normal[ax * 3 + 2]);
-        const float nn = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz))), 1e-12f);
-        nx = __fdiv_rn(nx, nn); ny = __fdiv_rn(ny, nn); nz = __fdiv_rn(nz, nn);
-        const float odn = __fadd_rn(__fadd_rn(__fmul_rn(ox, nx), __fmul_rn(oy, ny)), __fmul_rn(oz, nz));
-        float ddn = __fadd_rn(__fadd_rn(__fmul_rn(dx, nx), __fmul_rn(dy, ny)), __fmul_rn(dz, nz));
-        if (fabsf(ddn) < 1e-5f) ddn = 1e12f;
-        t = __fdiv_rn(__fsub_rn(pd, odn), ddn);
-      } else if (cfg.isect_type == HR_ISECT_DISTANCE) {
-        float zr = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, hz[j][0])), one_m);
-        float z = __fadd_rn(__fmul_rn(zr, cfg.z_scale), samp);
-        if (cfg.contract_samples) z = inv_contract_sample(cfg, dv, z);
-        t = __fadd_rn(z, base_distance);  // primitive.py:168-178
-      } else if (cfg.isect_type == HR_ISECT_SPHERE_NEW) {
-        // IntersectSphereNew (primitive.py:489-546): 8 channels per sample = origin 3, resize 3, offset 1, radius 1.  The
-        // last four are read here (the heads row sits in L1) so the other pipelines keep their register budget.
-        float zc[8];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) zc[c] = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, hz[j][c])), one_m);
-#pragma unroll
-        for (int c = 4; c < 8; ++c) {
-          const float raw = __ldg(hrow + (long long)(cfg.off_z + c) * S + (act ? s : 0));
-          zc[c] = __fmul_rn(apply_act(cfg.isect_act, apply_act(cfg.act_z, raw)), one_m);
-        }
-        float org[3], rsz[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          org[c] = __fmul_rn(zc[c], cfg.sphere_origin_scale);                                                        // :489-491
-          rsz[c] = __fadd_rn(__fmul_rn(zc[3 + c], cfg.sphere_resize_scale), cfg.sphere_resize_initial[c]);           // :493-495
-        }
-        float roff = __fadd_rn(__fmul_rn(zc[6], cfg.z_scale), samp);  // :501-502, both through process_z_vals
-        float rad = __fadd_rn(__fmul_rn(zc[7], cfg.z_scale), samp);
-        if (cfg.contract_samples) { roff = inv_contract_sample(cfg, dv, roff); rad = inv_contract_sample(cfg, dv, rad); }
-        // transformed ray (:512-521)
-        const float rox = __fmul_rn(__fsub_rn(ox, org[0]), rsz[0]), roy = __fmul_rn(__fsub_rn(oy, org[1]), rsz[1]),
-                    roz = __fmul_rn(__fsub_rn(oz, org[2]), rsz[2]);
-        const float rdx = __fmul_rn(dx, rsz[0]), rdy = __fmul_rn(dy, rsz[1]), rdz = __fmul_rn(dz, rsz[2]);
-        const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rdx, rdx), __fmul_rn(rdy, rdy)), __fmul_rn(rdz, rdz)));
-        const float nd = fmaxf(nrm, 1e-12f);  // F.normalize
-        const float ux = __fdiv_rn(rdx, nd), uy = __fdiv_rn(rdy, nd), uz = __fdiv_rn(rdz, nd);
-        // intersect_sphere (intersect_utils.py:45-84)
-        float tq;
-        {
-          const float oo = __fadd_rn(__fadd_rn(__fmul_rn(rox, rox), __fmul_rn(roy, roy)), __fmul_rn(roz, roz));
-          const float dd = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz));
-          const float od = __fadd_rn(__fadd_rn(__fmul_rn(rox, ux), __fmul_rn(roy, uy)), __fmul_rn(roz, uz));
-          const float a = dd, b = __fmul_rn(2.0f, od), c = __fsub_rn(oo, __fmul_rn(rad, rad));
-          float disc = __fsub_rn(__fmul_rn(b, b), __fmul_rn(__fmul_rn(4.0f, a), c));
-          disc = (disc < 0.0f) ? 0.0f : disc;
-          const float sq = sqrtf(__fadd_rn(disc, 1e-8f));
-          const float a2 = __fmul_rn(2.0f, a);
-          float t1 = __fdiv_rn(__fadd_rn(-b, sq), a2);
-          float t2 = __fdiv_rn(__fsub_rn(-b, sq), a2);
-          if (disc <= 0.0f) { t1 = 0.0f; t2 = 0.0f; }
-          tq = ((t2 < 0.0f) || (rad < 0.0f)) ? t1 : t2;
-        }
-        // min_sphere_radius (intersect_utils.py:27-33) and pluecker_pos (param.py:297-307) normalise the direction again
-        const float n2 = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 1e-12f);
-        const float vx = __fdiv_rn(ux, n2), vy = __fdiv_rn(uy, n2), vz = __fdiv_rn(uz, n2);
-        const float mx = __fsub_rn(__fmul_rn(roy, vz), __fmul_rn(roz, vy));  // m = cross(o, v)
-        const float my = __fsub_rn(__fmul_rn(roz, vx), __fmul_rn(rox, vz));
-        const float mz = __fsub_rn(__fmul_rn(rox, vy), __fmul_rn(roy, vx));
-        const float bx = __fsub_rn(__fmul_rn(vy, mz), __fmul_rn(vz, my));    // base = cross(v, m)
-        const float by = __fsub_rn(__fmul_rn(vz, mx), __fmul_rn(vx, mz));
-        const float bz = __fsub_rn(__fmul_rn(vx, my), __fmul_rn(vy, mx));
-        const float min_radius = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)), __fmul_rn(bz, bz)));
-        const float ex = __fsub_rn(bx, rox), ey = __fsub_rn(by, roy), ez = __fsub_rn(bz, roz);
-        const float dotde = __fadd_rn(__fadd_rn(__fmul_rn(ux, ex), __fmul_rn(uy, ey)), __fmul_rn(uz, ez));
-        const float sgn = (dotde > 0.0f) ? 1.0f : ((dotde < 0.0f) ? -1.0f : 0.0f);
-        const float base_distance = __fmul_rn(sgn, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez))));
-        // recycle samples of spheres the ray misses (:534-538), then back to world distances (:541)
-        if (fabsf(rad) < __fadd_rn(min_radius, __fmul_rn(4.0f, cfg.z_scale))) tq = __fadd_rn(roff, base_distance);
-        t = __fdiv_rn(tq, __fadd_rn(nrm, 1e-5f));
+      } else if (RARE && cfg.isect_type != HR_ISECT_SPHERE && cfg.isect_type != HR_ISECT_CYLINDER) {
+        // the less common primitives (sphere_new, euclidean_distance, voxel grids) live in one out-of-line function and are
+        // compiled into the RARE variants only: the z-plane / sphere / cylinder kernels keep their instruction stream and
+        // register budget (80 registers at three CTAs per SM)
+        t = intersect_rare(cfg, dv, hz[j][0], hz[j][1], hz[j][2], hz[j][3], one_m, samp, act ? s : 0, S, hrow, ox, oy, oz, dx, dy, dz);
       } else {
         float zc[4];
 #pragma unroll
@@ -760,7 +649,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         v = __fadd_rn(__fmul_rn(v, __fadd_rn(gs, 1.0f)), gb);
       }
     }
-    if (cfg.n_color_views > 0) {  // warp-uniform
+    if (RARE && cfg.n_color_views > 0) {  // warp-uniform; RARE variants only
       // transform_color_one (utils/tensorf_utils.py:308-331): rgb + M rgb + shift with the (M, shift) row of this ray's
       // camera, id = round(rays[:, -2]) (ColorTransformEmbedding.forward, point.py:594-605)
       const float v0 = __shfl_sync(kFull, v, sub * LW + 0);
@@ -794,7 +683,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
   }
 }
 
-template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE>
+template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool RARE>
 static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
                               const float* heads, const RgbDst& rgb, long long n, const ExtraOut* so, int num_sms,
                               cudaStream_t stream, unsigned char* rgb8) {
@@ -809,40 +698,46 @@ static cudaError_t launch_one(const hr_config& cfg, const Derived& dv, const Ren
   if (grid < 1) grid = 1;
   const dim3 g((unsigned)grid), b(kWarpsPerCta * 32);
   if (so) {
-    render_kernel<SPL, DYN, C0, C1, C2, SHADE, true, 1><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, *so, rgb8);
+    render_kernel<SPL, DYN, C0, C1, C2, SHADE, true, 1, RARE><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, *so, rgb8);
     return cudaGetLastError();
   }
   ExtraOut none{};
   if constexpr (SPL == 1) {
     if (two_rays) {
-      render_kernel<SPL, DYN, C0, C1, C2, SHADE, false, 2><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, none, rgb8);
+      render_kernel<SPL, DYN, C0, C1, C2, SHADE, false, 2, RARE><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, none, rgb8);
       return cudaGetLastError();
     }
   }
-  render_kernel<SPL, DYN, C0, C1, C2, SHADE, false, 1><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, none, rgb8);
+  render_kernel<SPL, DYN, C0, C1, C2, SHADE, false, 1, RARE><<<g, b, smem, stream>>>(cfg, dv, tabs, rays, heads, rgb, n, none, rgb8);
   return cudaGetLastError();
 }
 
-template <int SPL, bool DYN, int C0, int C1, int C2>
+template <int SPL, bool DYN, int C0, int C1, int C2, bool RARE>
 static cudaError_t launch_shade(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
                                 const float* heads, const RgbDst& rgb, long long n, const ExtraOut* so, int num_sms,
                                 cudaStream_t stream, unsigned char* rgb8) {
   if (cfg.shading == HR_SHADE_SH)
-    return launch_one<SPL, DYN, C0, C1, C2, HR_SHADE_SH>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
-  return launch_one<SPL, DYN, C0, C1, C2, HR_SHADE_RGB>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
+    return launch_one<SPL, DYN, C0, C1, C2, HR_SHADE_SH, RARE>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
+  return launch_one<SPL, DYN, C0, C1, C2, HR_SHADE_RGB, RARE>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
 }
 
-template <int SPL, bool DYN>
+// pipelines served by the RARE variants only (see render_kernel)
+static inline bool needs_rare(const hr_config& cfg) {
+  return (cfg.isect_type != HR_ISECT_Z_PLANE && cfg.isect_type != HR_ISECT_SPHERE && cfg.isect_type != HR_ISECT_CYLINDER) ||
+         cfg.n_color_views > 0;
+}
+
+template <int SPL, bool DYN, bool RARE>
 static cudaError_t launch_comps(const hr_config& cfg, const Derived& dv, const RenderTabs& tabs, const float* rays,
                                 const float* heads, const RgbDst& rgb, long long n, const ExtraOut* so, int num_sms,
                                 cudaStream_t stream, unsigned char* rgb8) {
   const int c0 = cfg.n_sigma[0], c1 = cfg.n_sigma[1], c2 = cfg.n_sigma[2];
   if (c0 == 8 && c1 == 0 && c2 == 0)
-    return launch_shade<SPL, DYN, 8, 0, 0>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
+    return launch_shade<SPL, DYN, 8, 0, 0, RARE>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
   if (c0 == 8 && c1 == 4 && c2 == 4)
-    return launch_shade<SPL, DYN, 8, 4, 4>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
+    return launch_shade<SPL, DYN, 8, 4, 4, RARE>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
   if (c0 == 8 && c1 == 8 && c2 == 8)
-    return launch_shade<SPL, DYN, 8, 8, 8>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
+    return launch_shade<SPL, DYN, 8, 8, 8, RARE>(cfg, dv, tabs, rays, heads, rgb, n, so, num_sms, stream, rgb8);
   return cudaErrorInvalidValue;
 }
 

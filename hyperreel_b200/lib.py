@@ -29,6 +29,7 @@ FIELDS = {"points": 0, "distances": 1, "base_times": 2, "time_offset": 3, "times
           "color_scale": 7, "color_shift": 8, "spatial_flow": 9, "sigma": 10, "point_sigma": 11, "point_offset": 12,
           "color_scale_global": 13, "color_shift_global": 14}
 FIELD_OVER, FIELD_NO_OVER, FIELD_PRED_WEIGHTS = 0, 1, 2
+PT_NONE, PT_POINT, PT_VIEW, PT_ORIGIN, PT_TIME = -1, 0, 3, 6, 9  # first channel of each source of the point net's input row
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libhyperreel_b200.so")
@@ -79,6 +80,14 @@ class hr_config(C.Structure):
         ("isect_axes", C.c_int32), ("z_scale3", C.c_float * 3), ("isect_outward", C.c_int32), ("isect_max_axis", C.c_int32),
         ("plane_normal", C.c_float * 9), ("plane_normal_scale", C.c_float),
         ("n_color_views", C.c_int32), ("act_ctransform", hr_act), ("act_ctshift", hr_act),
+        ("cascade", C.c_int32), ("pre_samples", C.c_int32), ("pre_n_groups", C.c_int32),
+        ("pre_groups", hr_encode_group * HR_MAX_GROUPS),
+        ("pre_mlp_in", C.c_int32), ("pre_mlp_width", C.c_int32), ("pre_mlp_layers", C.c_int32), ("pre_mlp_skip", C.c_int32),
+        ("pre_mlp_mode", C.c_int32), ("pre_head_stride", C.c_int32), ("pre_off_z", C.c_int32), ("pre_off_sigma", C.c_int32),
+        ("pre_act_z", hr_act), ("pre_act_sigma", hr_act), ("pre_isect_act", hr_act),
+        ("pre_use_sigma", C.c_int32), ("pre_sort", C.c_int32),
+        ("pre_z_scale", C.c_float), ("pre_near", C.c_float), ("pre_far", C.c_float),
+        ("pre_samples_tab", C.c_float * 32), ("pt_src", C.c_int32 * 8),
     ]
 
 
@@ -94,6 +103,7 @@ class hr_params(C.Structure):
         ("sigma_second", C.c_void_p * 3), ("app_second", C.c_void_p * 3),
         ("second_len", C.c_int32 * 3),
         ("basis_mat", C.c_void_p), ("color_embedding", C.c_void_p),
+        ("pre_mlp_weight", C.c_void_p * HR_MAX_LAYERS), ("pre_mlp_bias", C.c_void_p * HR_MAX_LAYERS),
     ]
 
 

@@ -87,7 +87,8 @@ class LightfieldModel(nn.Module):
         self.cur_iter = RENDER_ITER
         grid = kwargs.get("grid") or default_grid(self.sig)
         # reference-named parameter storage
-        self.embedding_model = _Embedding(self.sig.mlp_layer_shapes, self.sig.color_views, self.sig.color_embedding_index)
+        self.embedding_model = _Embedding(self.sig.mlp_layer_shapes, self.sig.color_views, self.sig.color_embedding_index,
+                                          self.sig.net_index, self.sig.pre_layer_shapes)
         self.color_model = _Color(self.sig, grid)
         self._lib = L.load_library()  # raises if the CUDA library is missing -- no fallback
         self._handle = C.c_void_p()
@@ -186,6 +187,8 @@ class LightfieldModel(nn.Module):
         kernels (hr_render_heads / hr_render_backward)."""
         rays = self._check_rays(rays)
         c = self.sig.cfg
+        if self.sig.cascade:
+            raise UnsupportedPipeline("cascaded (point_prediction) pipelines render on the fused path; their backward pass is not built")
         if clamp_output is None:
             clamp_output = not self.training
         if white_bg is None:
@@ -471,19 +474,26 @@ class LightfieldModel(nn.Module):
             return t.data_ptr()
 
         P.on_device = 1
-        net = self.embedding_model.embeddings[0].net
-        perm = list(self.sig.in_perm)
-        permuted = perm != list(range(len(perm)))
-        for i, layer in enumerate(getattr(net, "layers", [])):  # a `zero` sample net has no layers to upload
-            lin = layer[0] if isinstance(layer, nn.Sequential) else layer
-            w = lin.weight
-            if permuted and (i == 0 or i == self.sig.cfg.mlp_skip):
-                # BasicPE column order -> the kernels' per-band order (Signature.in_perm); the hidden part of the skip
-                # layer's input (cat([input, hidden]), mlp.py:167-168) keeps its place
-                cols = torch.tensor(perm + list(range(len(perm), w.shape[1])), device=w.device)
-                w = w.detach().index_select(1, cols)
-            P.mlp_weight[i] = dptr(w)
-            P.mlp_bias[i] = dptr(lin.bias)
+
+        def put_net(net, perm, skip_layer, weights, biases):
+            permuted = perm != list(range(len(perm)))
+            for i, layer in enumerate(getattr(net, "layers", [])):  # a `zero` sample net has no layers to upload
+                lin = layer[0] if isinstance(layer, nn.Sequential) else layer
+                w = lin.weight
+                if permuted and (i == 0 or i == skip_layer):
+                    # BasicPE column order -> the kernels' per-band order (Signature.in_perm); the hidden part of the skip
+                    # layer's input (cat([input, hidden]), mlp.py:167-168) keeps its place
+                    cols = torch.tensor(perm + list(range(len(perm), w.shape[1])), device=w.device)
+                    w = w.detach().index_select(1, cols)
+                weights[i] = dptr(w)
+                biases[i] = dptr(lin.bias)
+
+        # the net behind the final heads: the ray_prediction net, or the point_prediction net of a cascaded pipeline
+        put_net(self.embedding_model.embeddings[self.sig.net_index].net, list(self.sig.in_perm), self.sig.cfg.mlp_skip,
+                P.mlp_weight, P.mlp_bias)
+        if self.sig.cascade:
+            put_net(self.embedding_model.embeddings[0].net, list(self.sig.pre_in_perm), self.sig.cfg.pre_mlp_skip,
+                    P.pre_mlp_weight, P.pre_mlp_bias)
         tn = self.color_model.net
         dplane, dsecond, aplane, asecond = tn.tables()
         for i in range(3):

@@ -90,6 +90,12 @@ class Signature:
     # `embeddings` ModuleList (state_dict name model.embedding_model.embeddings.{index}.color_embedding)
     color_views: int = 0
     color_embedding_index: int = -1
+    # cascaded pipelines: `mlp_layer_shapes` / `in_perm` describe the point net, stored at embeddings.{net_index}.net; the
+    # first-stage ray net (embeddings.0.net) has pre_layer_shapes ([] for a `zero` net) / pre_in_perm
+    cascade: bool = False
+    net_index: int = 0
+    pre_layer_shapes: List[tuple] = field(default_factory=list)
+    pre_in_perm: List[int] = field(default_factory=list)
 
     @property
     def c_in(self) -> int:
@@ -138,11 +144,17 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     seq = [e for e in seq if e.type != "color_transform"]
     types = [e.type for e in seq]
     expect = ["ray_prediction", "ray_intersect"]
-    rest = types[2:]
+    # cascaded pipelines (PointPredictionEmbedding, point.py:39-219): a second net runs at the points of a first, coarse
+    # intersection and predicts the primitives of the second one
+    cascade = types[2:4] == ["point_prediction", "ray_intersect"]
+    rest = types[4:] if cascade else types[2:]
     allowed_tail = [t for t in ("advect_points", "point_offset", "add_point_outputs", "extract_fields") if t in rest]
     if types[:2] != expect or rest != allowed_tail or "add_point_outputs" not in rest or "extract_fields" not in rest:
         raise UnsupportedPipeline(f"embedding sequence {types} is not a recognised pipeline")
-    pred, isect = seq[0], seq[1]
+    pred0, isect0 = seq[0], seq[1]
+    # `pred` / `isect`: the prediction whose outputs are the heads the colour net's samples come from, and their intersection
+    pred, isect = (seq[2], seq[3]) if cascade else (seq[0], seq[1])
+    point_index = next((i for i, k in enumerate(embs.keys()) if embs[k] is pred), 0) if cascade else 0
     flow = next((e for e in seq if e.type == "advect_points"), None)
     offset = next((e for e in seq if e.type == "point_offset"), None)
     addp = next(e for e in seq if e.type == "add_point_outputs")
@@ -153,96 +165,136 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
         raise UnsupportedPipeline(f"colour net '{net.type}' is not on the fused path")
     dynamic = net.type == "tensor_vm_split_time"
 
-    # ------------------------------------------------------------------ sample-net input (ray.py:235-263)
-    max_end = 6
-    groups = []
-    mlp_in = 0
-    in_perm: List[int] = []
-    for key in pred.params.keys():
-        p = pred.params[key]
-        g = L.hr_encode_group()
-        g.start, g.end = int(p.start), int(p.end)
-        max_end = max(max_end, g.end)
-        fn = p.param.fn
-        if fn == "identity":
-            g.fn, dims = L.PARAM_IDENTITY, g.end - g.start
-        elif fn == "two_plane":
-            g.fn, dims = L.PARAM_TWO_PLANE, 4
-            if any(k in p.param for k in ("origin", "use_local_param")) or g.end - g.start != 6:
-                raise UnsupportedPipeline("two_plane: origin/local param not supported")
-        elif fn == "pluecker":
-            g.fn, dims = L.PARAM_PLUECKER, 6
-            if any(k in p.param for k in ("origin", "use_local_param")) or g.end - g.start != 6:
-                raise UnsupportedPipeline("pluecker: origin/local param not supported")
-        else:
-            raise UnsupportedPipeline(f"ray param '{fn}' is not on the fused path")
-        if dims > 8:
-            raise UnsupportedPipeline("param group wider than 8 channels")
-        g.near, g.far = float(_get(p.param, "near", -1.0)), float(_get(p.param, "far", 0.0))
-        g.dir_mult = float(_get(p.param, "direction_multiplier", 1.0))
-        g.mom_mult = float(_get(p.param, "moment_multiplier", 1.0))
-        pe = _get(p, "pe")
-        g.n_freqs, g.exclude_identity, g.freq_mult, g.base_mult = 0, 0, 2.0, 1.0
-        if pe is not None and pe.type == "basic":
-            # BasicPE (pe.py:32-68): same values as a fully open WindowedPE, other column order (handled by in_perm)
-            g.n_freqs = int(pe.n_freqs)
-            g.freq_mult = float(_get(pe, "freq_multiplier", 2.0))
-            D, Fq, k0 = dims, g.n_freqs, mlp_in
-            for i in range(D):
-                in_perm.append(k0 + i)
-            for f in range(Fq):
+    # ------------------------------------------------------------------ sample-net input (ray.py:235-263, point.py:69-100)
+    def encode_groups(params):
+        max_end = 6
+        groups = []
+        mlp_in = 0
+        in_perm: List[int] = []
+        for key in params.keys():
+            p = params[key]
+            g = L.hr_encode_group()
+            g.start, g.end = int(p.start), int(p.end)
+            max_end = max(max_end, g.end)
+            fn = p.param.fn
+            if fn == "identity":
+                g.fn, dims = L.PARAM_IDENTITY, g.end - g.start
+            elif fn == "two_plane":
+                g.fn, dims = L.PARAM_TWO_PLANE, 4
+                if any(k in p.param for k in ("origin", "use_local_param")) or g.end - g.start != 6:
+                    raise UnsupportedPipeline("two_plane: origin/local param not supported")
+            elif fn == "pluecker":
+                g.fn, dims = L.PARAM_PLUECKER, 6
+                if any(k in p.param for k in ("origin", "use_local_param")) or g.end - g.start != 6:
+                    raise UnsupportedPipeline("pluecker: origin/local param not supported")
+            else:
+                raise UnsupportedPipeline(f"ray param '{fn}' is not on the fused path")
+            if dims > 8:
+                raise UnsupportedPipeline("param group wider than 8 channels")
+            g.near, g.far = float(_get(p.param, "near", -1.0)), float(_get(p.param, "far", 0.0))
+            g.dir_mult = float(_get(p.param, "direction_multiplier", 1.0))
+            g.mom_mult = float(_get(p.param, "moment_multiplier", 1.0))
+            pe = _get(p, "pe")
+            g.n_freqs, g.exclude_identity, g.freq_mult, g.base_mult = 0, 0, 2.0, 1.0
+            if pe is not None and pe.type == "basic":
+                # BasicPE (pe.py:32-68): same values as a fully open WindowedPE, other column order (handled by in_perm)
+                g.n_freqs = int(pe.n_freqs)
+                g.freq_mult = float(_get(pe, "freq_multiplier", 2.0))
+                D, Fq, k0 = dims, g.n_freqs, mlp_in
                 for i in range(D):
-                    in_perm.append(k0 + D + i * Fq + f)            # sin(band f, dim i)
-                for i in range(D):
-                    in_perm.append(k0 + D + D * Fq + i * Fq + f)   # cos(band f, dim i)
-        elif pe is not None:
-            if pe.type != "windowed":
-                raise UnsupportedPipeline(f"pe type '{pe.type}' is not on the fused path")
-            # all windows must be open (pe.py:186-196): cur_iter past wait and past max_freq_iter
-            mfi = float(_get(pe, "max_freq_iter", 0))
-            if "window_iters" in pe:
-                mfi = max(max(w) for w in pe.window_iters)
-            if (cur_iter - _get(pe, "wait_iters", 0)) < 0 or (mfi != 0 and not cur_iter > mfi):
-                raise UnsupportedPipeline("windowed PE not fully open at this iteration")
-            if _get(pe, "ceil", False) or _get(pe, "window_identity", False):
-                pass  # irrelevant once every weight is 1
-            g.n_freqs = int(pe.n_freqs)
-            g.exclude_identity = int(bool(_get(pe, "exclude_identity", False)))
-            g.freq_mult = float(_get(pe, "freq_multiplier", 2.0))
-            g.base_mult = float(_get(pe, "base_multiplier", 1.0))
-        if not (pe is not None and pe.type == "basic"):
-            n_feat = dims * (2 * g.n_freqs + (0 if g.exclude_identity else 1))
-            in_perm.extend(range(mlp_in, mlp_in + n_feat))
-        mlp_in += dims * (2 * g.n_freqs + (0 if g.exclude_identity else 1))
-        groups.append(g)
-    if len(groups) > L.HR_MAX_GROUPS:
-        raise UnsupportedPipeline("too many param groups")
+                    in_perm.append(k0 + i)
+                for f in range(Fq):
+                    for i in range(D):
+                        in_perm.append(k0 + D + i * Fq + f)            # sin(band f, dim i)
+                    for i in range(D):
+                        in_perm.append(k0 + D + D * Fq + i * Fq + f)   # cos(band f, dim i)
+            elif pe is not None:
+                if pe.type != "windowed":
+                    raise UnsupportedPipeline(f"pe type '{pe.type}' is not on the fused path")
+                # all windows must be open (pe.py:186-196): cur_iter past wait and past max_freq_iter
+                mfi = float(_get(pe, "max_freq_iter", 0))
+                if "window_iters" in pe:
+                    mfi = max(max(w) for w in pe.window_iters)
+                if (cur_iter - _get(pe, "wait_iters", 0)) < 0 or (mfi != 0 and not cur_iter > mfi):
+                    raise UnsupportedPipeline("windowed PE not fully open at this iteration")
+                if _get(pe, "ceil", False) or _get(pe, "window_identity", False):
+                    pass  # irrelevant once every weight is 1
+                g.n_freqs = int(pe.n_freqs)
+                g.exclude_identity = int(bool(_get(pe, "exclude_identity", False)))
+                g.freq_mult = float(_get(pe, "freq_multiplier", 2.0))
+                g.base_mult = float(_get(pe, "base_multiplier", 1.0))
+            if not (pe is not None and pe.type == "basic"):
+                n_feat = dims * (2 * g.n_freqs + (0 if g.exclude_identity else 1))
+                in_perm.extend(range(mlp_in, mlp_in + n_feat))
+            mlp_in += dims * (2 * g.n_freqs + (0 if g.exclude_identity else 1))
+            groups.append(g)
+        if len(groups) > L.HR_MAX_GROUPS:
+            raise UnsupportedPipeline("too many param groups")
+        return groups, mlp_in, in_perm, max_end
+
+    groups, mlp_in, in_perm, max_end = encode_groups(pred.params)
     c.n_groups = len(groups)
     for i, g in enumerate(groups):
         c.groups[i] = g
+    pre_in_perm: List[int] = []
+    if cascade:
+        if max_end > 8:
+            raise UnsupportedPipeline("point_prediction: param group reads beyond the 8-channel input row")
+        groups0, mlp_in0, pre_in_perm, max_end = encode_groups(pred0.params)
+        c.pre_n_groups, c.pre_mlp_in = len(groups0), mlp_in0
+        for i, g in enumerate(groups0):
+            c.pre_groups[i] = g
     c.c_in = 8 if (dynamic or flow is not None or max_end > 6) else 6
     if max_end > c.c_in:
         raise UnsupportedPipeline("param group reads beyond the ray")
 
     # ------------------------------------------------------------------ sample net (mlp.py:60-178)
-    ncfg = pred.net
-    if ncfg.type not in ("base", "zero"):
-        raise UnsupportedPipeline(f"sample net '{ncfg.type}' is not on the fused path")
-    zero_net = ncfg.type == "zero"  # ZeroMLP (nlf/nets/mlp.py:14-33): every head is 0 before its activation
-    if zero_net:
-        c.mlp_mode = L.MLP_ZERO
-    for k in ("pe", "latent_dim", "pad_to", "is_constant", "zero_before_channel", "pe_channels"):
-        if k in ncfg:
-            raise UnsupportedPipeline(f"sample net option '{k}' is not on the fused path")
-    if _get(ncfg, "activation", "identity") != "identity" or _get(ncfg, "layer_activation", "leaky_relu") != "leaky_relu":
-        raise UnsupportedPipeline("sample net activations must be leaky_relu / identity")
-    if not _get(ncfg, "bias", True):
-        raise UnsupportedPipeline("bias-free sample net")
-    depth = int(ncfg.depth)  # RayPredictionEmbedding: depth -= 2, linear_last=False -> `depth` Linear layers
-    skips = list(_get(ncfg, "skips", []))
-    if len(skips) > 1:
-        raise UnsupportedPipeline("more than one skip connection")
-    S = int(pred.z_channels)
+    def net_shape(ncfg, n_in, n_out):
+        """BaseMLP / ZeroMLP behind a prediction embedding -> (zero, width, depth, skip, [(out, in) per Linear])."""
+        if ncfg.type not in ("base", "zero"):
+            raise UnsupportedPipeline(f"sample net '{ncfg.type}' is not on the fused path")
+        zero = ncfg.type == "zero"  # ZeroMLP (nlf/nets/mlp.py:14-33): every head is 0 before its activation
+        if zero:
+            return True, int(_get(ncfg, "hidden_channels", 0)), int(_get(ncfg, "depth", 0)), -1, []
+        for k in ("pe", "latent_dim", "pad_to", "is_constant", "zero_before_channel", "pe_channels"):
+            if k in ncfg:
+                raise UnsupportedPipeline(f"sample net option '{k}' is not on the fused path")
+        if _get(ncfg, "activation", "identity") != "identity" or _get(ncfg, "layer_activation", "leaky_relu") != "leaky_relu":
+            raise UnsupportedPipeline("sample net activations must be leaky_relu / identity")
+        if not _get(ncfg, "bias", True):
+            raise UnsupportedPipeline("bias-free sample net")
+        depth = int(ncfg.depth)  # Ray/PointPredictionEmbedding: depth -= 2, linear_last=False -> `depth` Linear layers
+        skips = list(_get(ncfg, "skips", []))
+        if len(skips) > 1:
+            raise UnsupportedPipeline("more than one skip connection")
+        W = int(ncfg.hidden_channels)
+        if W not in (128, 256):
+            raise UnsupportedPipeline(f"sample net hidden width {W} is not on the fused path (128 or 256)")
+        if n_in > 64:
+            raise UnsupportedPipeline(f"sample net input of {n_in} encoded features is not on the fused path (<= 64)")
+        if not (2 <= depth <= L.HR_MAX_LAYERS):
+            raise UnsupportedPipeline(f"sample net depth {depth} is not on the fused path")
+        skip = int(skips[0]) if skips else -1
+        shp = []
+        for i in range(depth):
+            fin = n_in if i == 0 else (W + n_in if i == skip else W)
+            shp.append((n_out if i == depth - 1 else W, fin))
+        return False, W, depth, skip, shp
+
+    if cascade:
+        # PointPredictionEmbedding (point.py:39-140): in_z_channels points per ray, out_z_channels samples per ray
+        S, S0 = int(_get(pred, "out_z_channels", 1)), int(_get(pred, "in_z_channels", 1))
+        if int(pred0.z_channels) != S0 or int(isect0.z_channels) != S0:
+            raise UnsupportedPipeline("point_prediction: in_z_channels must equal the first stage's z_channels")
+        if S0 < 1 or S0 > 32 or S % S0 != 0:
+            raise UnsupportedPipeline(f"point_prediction: {S0} points per ray / {S} samples per ray is not on the fused path")
+        for k in ("filter", "rays_name", "points_name"):
+            if _get(pred, k, False) not in (False, "rays", "points"):
+                raise UnsupportedPipeline(f"point_prediction option '{k}' is not on the fused path")
+        if any(bool(_get(pred.outputs[k], "residual", False)) for k in pred.outputs.keys()):
+            raise UnsupportedPipeline("point_prediction: residual outputs are not on the fused path")
+    else:
+        S = int(pred.z_channels)
     if int(isect.z_channels) != S:
         raise UnsupportedPipeline("z_channels mismatch between prediction and intersection")
     if "ray_outputs" in pred and len(pred.ray_outputs) > 0:
@@ -250,25 +302,16 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     head_names = list(pred.outputs.keys())
     head_channels = [int(pred.outputs[k].channels) for k in head_names]
     stride = sum(head_channels)
-    c.mlp_in, c.mlp_width, c.mlp_layers = mlp_in, int(ncfg.hidden_channels), depth
-    if zero_net:
-        pass
-    elif c.mlp_width not in (128, 256):
-        raise UnsupportedPipeline(f"sample net hidden width {c.mlp_width} is not on the fused path (128 or 256)")
-    if mlp_in > 64 and not zero_net:
-        raise UnsupportedPipeline(f"sample net input of {mlp_in} encoded features is not on the fused path (<= 64)")
-    if not (2 <= depth <= L.HR_MAX_LAYERS) and not zero_net:
-        raise UnsupportedPipeline(f"sample net depth {depth} is not on the fused path")
-    c.mlp_skip = int(skips[0]) if skips else -1
     c.mlp_out = S * stride
     c.leaky_slope = 0.01
     c.n_samples, c.head_stride = S, stride
-    W = c.mlp_width
-    shapes = []
-    for i in range(0 if zero_net else depth):
-        fin = mlp_in if i == 0 else (W + mlp_in if i == c.mlp_skip else W)
-        fout = c.mlp_out if i == depth - 1 else W
-        shapes.append((fout, fin))
+    # the net's output row: all S samples of a ray, or the S / S0 samples one first-stage point expands to
+    zero_net, W, depth, c.mlp_skip, shapes = net_shape(pred.net, mlp_in, (S // S0) * stride if cascade else c.mlp_out)
+    if zero_net and cascade:
+        raise UnsupportedPipeline("point_prediction with a zero net")
+    if zero_net:
+        c.mlp_mode = L.MLP_ZERO
+    c.mlp_in, c.mlp_width, c.mlp_layers = mlp_in, W, depth
 
     # ------------------------------------------------------------------ heads (ray.py:331-337)
     offs: Dict[str, int] = {}
@@ -295,6 +338,68 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     c.act_z, c.act_flow, c.act_sigma = act_of("z_vals"), act_of("spatial_flow"), act_of("sigma")
     c.act_point_sigma, c.act_offset = act_of("point_sigma"), act_of("point_offset")
     c.act_cscale, c.act_cshift = act_of("color_scale"), act_of("color_shift")
+
+    # ------------------------------------------------------------------ first stage of a cascade (ray net -> z-planes -> points)
+    c.cascade, c.pre_samples = int(cascade), 0
+    for k in range(8):
+        c.pt_src[k] = L.PT_NONE
+    pre_shapes: List[tuple] = []
+    if cascade:
+        c.pre_samples = S0
+        names0 = list(pred0.outputs.keys())
+        ch0 = [int(pred0.outputs[k].channels) for k in names0]
+        if any(nme not in ("z_vals", "sigma") for nme in names0) or "z_vals" not in names0 or any(ch != 1 for ch in ch0):
+            raise UnsupportedPipeline("first stage of a cascade: one-channel z_vals (and sigma) heads only")
+        if "ray_outputs" in pred0 and len(pred0.ray_outputs) > 0:
+            raise UnsupportedPipeline("per-ray outputs are not on the fused path")
+        c.pre_head_stride = len(names0)
+        c.pre_off_z, c.pre_off_sigma = names0.index("z_vals"), (names0.index("sigma") if "sigma" in names0 else -1)
+        c.pre_act_z = resolve_activation(_get(pred0.outputs["z_vals"], "activation"), cur_iter)
+        c.pre_act_sigma = (resolve_activation(_get(pred0.outputs["sigma"], "activation"), cur_iter) if "sigma" in names0
+                           else L.hr_act(0, 1.0, 0.0, 1.0))
+        zero0, c.pre_mlp_width, c.pre_mlp_layers, c.pre_mlp_skip, pre_shapes = net_shape(pred0.net, c.pre_mlp_in, S0 * c.pre_head_stride)
+        c.pre_mlp_mode = L.MLP_ZERO if zero0 else int(mlp_mode)
+        it0 = isect0.intersect
+        if it0.type != "z_plane":
+            raise UnsupportedPipeline(f"first stage of a cascade: intersect '{it0.type}' (z_plane only)")
+        for k in ("origin", "weight_fn", "sort_outputs", "dropout", "use_disparity", "residual_z", "residual_distance", "normalize",
+                  "clamp", "forward_facing", "contract", "z_scale", "num_samples_for_scale"):
+            if k in it0 and it0[k] not in (False, None):
+                raise UnsupportedPipeline(f"first stage of a cascade: intersect option '{k}' is not on the fused path")
+        use_ds0 = bool(_get(it0, "use_dataset_bounds", False))
+        if use_ds0:  # z.py:26-31
+            lo0, hi0 = torch.tensor(-ds["near"]), torch.tensor(-ds["far"])
+        else:
+            lo0, hi0 = torch.tensor(_get(it0, "initial", 0.0)), torch.tensor(_get(it0, "end", 1.0))
+        tab0 = torch.linspace(float(lo0.float()), float(hi0.float()), S0)
+        for i in range(S0):
+            c.pre_samples_tab[i] = float(tab0[i])
+        c.pre_z_scale = float(torch.abs(tab0[1] - tab0[0])) if S0 > 1 else 1.0
+        c.pre_near = float(_get(it0, "near", ds["near"] if use_ds0 else 0.0))
+        c.pre_far = float(_get(it0, "far", float("inf")))
+        if "mask" in it0 and it0.mask is not None and cur_iter > float(_get(it0.mask, "stop_iters", float("inf"))):
+            c.pre_near, c.pre_far = float("-inf"), float("inf")  # base.py:104-105,197-198
+        c.pre_sort = int(bool(_get(it0, "sort", False)))
+        c.pre_isect_act = resolve_activation(_get(it0, "activation", "identity"), cur_iter)
+        c.pre_use_sigma = int(bool(_get(it0, "use_sigma", False)) and _get(it0, "in_density_field", "sigma") == "sigma"
+                              and "sigma" in names0)
+        # the point net's input row (point.py:151-160): the named tensors concatenated in YAML order
+        src, k = {"points": L.PT_POINT, "viewdirs": L.PT_VIEW, "origins": L.PT_ORIGIN}, 0
+        for nme in pred.inputs.keys():
+            width = int(pred.inputs[nme])
+            if nme == "times":
+                chans = [L.PT_TIME]  # rays[..., -1:]: one channel whatever the configured width
+            elif nme in src and 1 <= width <= 3:
+                chans = [src[nme] + j for j in range(width)]
+            else:
+                raise UnsupportedPipeline(f"point_prediction input '{nme}' is not on the fused path")
+            for ch in chans:
+                if k >= 8:
+                    raise UnsupportedPipeline("point_prediction: more than 8 input channels")
+                c.pt_src[k] = ch
+                k += 1
+        if max(int(g.end) for g in groups) > k:
+            raise UnsupportedPipeline("point_prediction: param group reads beyond its inputs")
 
     # ------------------------------------------------------------------ intersection (base.py:52-126, z.py, primitive.py)
     it = isect.intersect
@@ -608,4 +713,5 @@ def lower(model_cfg, dataset: dict, cur_iter: int = RENDER_ITER, iters_per_epoch
     c.clamp_output = 1
     return Signature(cfg=c, model_cfg=m, dataset=ds, head_names=head_names, head_channels=head_channels,
                      mlp_layer_shapes=shapes, dynamic=dynamic, in_perm=in_perm, color_views=color_views,
-                     color_embedding_index=ctrans_index)
+                     color_embedding_index=ctrans_index, cascade=cascade, net_index=point_index,
+                     pre_layer_shapes=pre_shapes, pre_in_perm=pre_in_perm)

@@ -55,14 +55,18 @@ class _ColorTransform(nn.Module):
 
 class _Embedding(nn.Module):
     """`embeddings` mirrors RayPointEmbedding's ModuleList (nlf/embedding/embedding.py:80-96): one entry per YAML key, in
-    order; entries without parameters are empty modules (they add no state_dict keys)."""
+    order; entries without parameters are empty modules (they add no state_dict keys).  Entry 0 is the ray_prediction; a
+    cascaded pipeline has its point_prediction net at `net_index` (then `shapes` is that net's and `pre_shapes` the ray net's,
+    [] for a `zero` net); a colour transform sits at `color_index`."""
 
-    def __init__(self, shapes, color_views: int = 0, color_index: int = -1):
+    def __init__(self, shapes, color_views: int = 0, color_index: int = -1, net_index: int = 0, pre_shapes=None):
         super().__init__()
-        mods = [_Prediction(shapes)]
+        entries = {0: _Prediction(shapes if net_index == 0 else (pre_shapes or []))}
+        if net_index > 0:
+            entries[net_index] = _Prediction(shapes)
         if color_views > 0 and color_index > 0:
-            mods += [nn.Module() for _ in range(color_index - 1)] + [_ColorTransform(color_views)]
-        self.embeddings = nn.ModuleList(mods)
+            entries[color_index] = _ColorTransform(color_views)
+        self.embeddings = nn.ModuleList([entries.get(i, nn.Module()) for i in range(max(entries) + 1)])
 
 
 class _Tensorf(nn.Module):
@@ -167,7 +171,7 @@ def seeded_state_dict(sig: Signature, grid: Optional[Sequence[int]] = None, seed
     grid = list(grid) if grid is not None else default_grid(sig)
     with torch.random.fork_rng(devices=[]):
         torch.manual_seed(seed)
-        emb = _Embedding(sig.mlp_layer_shapes, sig.color_views, sig.color_embedding_index)
+        emb = _Embedding(sig.mlp_layer_shapes, sig.color_views, sig.color_embedding_index, sig.net_index, sig.pre_layer_shapes)
         if sig.color_views > 0:  # the reference initialises the table with zeros (identity transform): give the tests something to see
             emb.embeddings[sig.color_embedding_index].color_embedding.data.normal_(0.0, 0.5)
         col = _Color(sig, grid)

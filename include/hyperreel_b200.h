@@ -164,7 +164,29 @@ typedef struct hr_config {
    * 0 = off (no such embedding, or the dataset does not validate on every camera) */
   int32_t n_color_views;
   hr_act act_ctransform, act_ctshift;
+
+  /* --- cascaded pipelines (PointPredictionEmbedding, nlf/embedding/point.py:39-219) ---
+   * cascade == 1:  ray_prediction -> ray_intersect (pre_samples z-planes) -> point_prediction -> ray_intersect -> ...
+   * The fields above then describe the SECOND stage: `groups` / `mlp_*` are the point net (evaluated once per first-stage
+   * point on the 8-float row pt_src describes, emitting n_samples / pre_samples samples each, :142-206), the heads and the
+   * intersection are those of the second ray_intersect.  The first stage -- a ray net or none, z-planes only -- is: */
+  int32_t cascade;
+  int32_t pre_samples;                      /* S0 = z_channels of the first stage (<= 32, divides n_samples)             */
+  int32_t pre_n_groups;
+  hr_encode_group pre_groups[HR_MAX_GROUPS];
+  int32_t pre_mlp_in, pre_mlp_width, pre_mlp_layers, pre_mlp_skip;
+  int32_t pre_mlp_mode;                     /* HR_MLP_ZERO or the same mode as mlp_mode                                  */
+  int32_t pre_head_stride, pre_off_z, pre_off_sigma;  /* first-stage heads: z_vals (1 channel) and optionally sigma      */
+  hr_act pre_act_z, pre_act_sigma, pre_isect_act;
+  int32_t pre_use_sigma, pre_sort;
+  float pre_z_scale, pre_near, pre_far;     /* like z_scale / isect_near / isect_far                                     */
+  float pre_samples_tab[32];
+  int32_t pt_src[8];                        /* HR_PT_*: what channel k of the point net's input row holds (:151-160)     */
 } hr_config;
+
+/* sources of the point net's inputs (`inputs:` of point_prediction; the named tensors are concatenated in YAML order) */
+enum { HR_PT_NONE = -1, HR_PT_POINT_X = 0, HR_PT_POINT_Y = 1, HR_PT_POINT_Z = 2, HR_PT_VIEW_X = 3, HR_PT_VIEW_Y = 4,
+       HR_PT_VIEW_Z = 5, HR_PT_ORIGIN_X = 6, HR_PT_ORIGIN_Y = 7, HR_PT_ORIGIN_Z = 8, HR_PT_TIME = 9 };
 
 /* Parameters in the reference's own state_dict layout, fp32, contiguous.
  * hr_upload re-lays them out on the device (channel-last tables, packed / split net weights) into
@@ -185,6 +207,9 @@ typedef struct hr_params {
   int32_t second_len[3];                 /* L_i                                          */
   const float* basis_mat;                /* basis_mat.weight [app_dim, sum(n_app)]       */
   const float* color_embedding;          /* embeddings.{i}.color_embedding [n_color_views, 12] (NULL when n_color_views == 0) */
+  /* cascade: the first-stage ray net (embeddings.0.net); mlp_weight / mlp_bias above are then the point net's */
+  const float* pre_mlp_weight[HR_MAX_LAYERS];
+  const float* pre_mlp_bias[HR_MAX_LAYERS];
 } hr_params;
 
 typedef struct hr_handle hr_handle;

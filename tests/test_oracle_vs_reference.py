@@ -120,15 +120,15 @@ def test_oracle_matches_reference_on_every_shipped_yaml_that_lowers():
         assert float((a.reshape(b.shape) - b).abs().max()) <= 2e-6, os.path.basename(f)
         checked += 1
         nonzero += int(float(b.abs().max()) > 0)
-    assert checked >= 41 and nonzero >= 36
+    assert checked >= 45 and nonzero >= 40
 
 
-def test_seven_shipped_yamls_do_not_run_in_the_reference_itself():
+def test_six_shipped_yamls_do_not_run_in_the_reference_itself():
     """Coverage ledger honesty: catacaustics_sphere / refnerf_sphere (8 z channels into the 4-channel `sphere` primitive),
     shiny_z_tensorf (`z` is not a registered intersect type), donerf_z / shiny_z_depth (`epipolar` is not a registered embedding
-    type), blender_voxel (its ray_prediction has no `params`) and shiny_z_tensorf_cascaded (a string threshold compared with a
-    tensor) fail inside the unmodified reference, so no implementation can be held to them; together with the empty
-    bom_z_plane.yaml they are excluded from the denominator in DESIGN.md section 7."""
+    type) and blender_voxel (its ray_prediction has no `params`) fail inside the unmodified reference, so no implementation can
+    be held to them; together with the empty bom_z_plane.yaml they are excluded from the denominator in DESIGN.md section 7.
+    (The YAMLs are read like Hydra / OmegaConf reads them: `1e-4` is a float, hyperreel_b200/config.py:_yaml_loader.)"""
     import hyperreel_b200 as hb
     from hyperreel_b200.config import to_plain
 
@@ -136,8 +136,7 @@ def test_seven_shipped_yamls_do_not_run_in_the_reference_itself():
     from nlf.rendering import render_chunked
 
     ds = {"num_keyframes": 12, "num_frames": 50, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y"}
-    for name in ("catacaustics_sphere", "refnerf_sphere", "shiny_z_tensorf", "donerf_z", "shiny_z_depth", "blender_voxel",
-                 "shiny_z_tensorf_cascaded"):
+    for name in ("catacaustics_sphere", "refnerf_sphere", "shiny_z_tensorf", "donerf_z", "shiny_z_depth", "blender_voxel"):
         cfg = hb.load_model_yaml(f"{ref_shim.REFERENCE_ROOT}/conf/experiment/model/{name}.yaml")
         cfg.color.net.N_voxel_init = cfg.color.net.N_voxel_final = 16 ** 3
         rays = torch.randn(8, 6) * 0.3

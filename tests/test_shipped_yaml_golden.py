@@ -30,7 +30,7 @@ def load_fixture(path):
 
 
 def test_fixture_set_is_complete():
-    assert len(SHIPPED) == 41
+    assert len(SHIPPED) == 45
 
 
 @pytest.mark.parametrize("path", SHIPPED, ids=[os.path.basename(p)[:-4] for p in SHIPPED])
