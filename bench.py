@@ -460,7 +460,7 @@ def run_ours(args):
     strong = None
     if world > 1:
         strong = []
-        for total in (65536, 4194304):
+        for total in (65536, 262144, 1048576, 4194304):  # BASELINE config 5: the 65k - 4M sweep
             rs = torch.cat([hb.rays.for_signature(sig, min(total, 1 << 20), seed=77)] * max(1, total >> 20), 0)[:total].to(dev)
 
             def sstep():
@@ -478,6 +478,33 @@ def run_ours(args):
             strong.append({"rays_total": total, "rays_per_gpu": total // world, "ms_per_step": float(ms.item()),
                            "value": total / (float(ms.item()) * 1e-3) / 1e6, "unit": "Mrays/s", "steps": k})
             del rs
+    # ---- BASELINE config 4: one full Neural-3D frame (2704 x 2028 rays, 64 samples) ray-sharded over the ranks ----
+    frame = None
+    if world > 1 and not args.no_extras:
+        spec = EXTRA_WORKLOADS["neural3d_s64"]
+        _, fcfg, fds, fsig, fsd = build_workload(spec["builtin"], spec["over"], gain=100.0, app_gain=6.0)
+        fmodel, frender = make_render(hb, fcfg, fds, fsd)
+        total = 2704 * 2028
+        fr = torch.cat([hb.rays.for_signature(fsig, 1 << 20, seed=91)] * 6, 0)[:total].to(dev)
+
+        def fstep():
+            return render_sharded(fr, frender)
+
+        for _ in range(2):
+            got = fstep()
+        torch.cuda.synchronize()
+        lo = (rank * 104729) % (total - 4096)
+        assert torch.equal(got[lo:lo + 4096], frender(fr[lo:lo + 4096])["rgb"]), "frame tiles differ from a local re-render"
+        dist.barrier()
+        k = 3
+        ms = torch.tensor([timed_steps(torch, fstep, k, flush) / k], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        frame = {"workload": "Neural-3D shape (BASELINE config 4): full 2704x2028 frame, 64 samples/ray, grid 823x617x514, K=12, comps [8,4,4], "
+                             "SH-27, ray-sharded over the ranks through render_sharded", "rays_total": total,
+                 "rays_per_gpu": total // world, "ms_per_frame": float(ms.item()), "frames_per_s": 1e3 / float(ms.item()),
+                 "value": total / (float(ms.item()) * 1e-3) / 1e6, "unit": "Mrays/s", "steps": k}
+        del fr, fmodel, frender
+        torch.cuda.empty_cache()
     # the timed regions last a few milliseconds, far less than one nvidia-smi poll: keep the same step running for about
     # 1.5 s more (a fixed count, so that every rank issues the same number of barriers) so that the clock /
     # throttle-reason samples are taken under this load
@@ -549,6 +576,8 @@ def run_ours(args):
             line["extra_workloads"] = extras
         if strong is not None:
             line["strong"] = strong
+        if frame is not None:
+            line["frame_neural3d"] = frame
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -631,8 +631,8 @@ static int64_t sub_batch_rays(const hr_handle* h) {
 static int64_t cascade_bytes(const hr_handle* h, int64_t n_rays) {
   const hr_config& c = h->cfg;
   if (!c.cascade) return 0;
-  const int64_t per_ray = (int64_t)c.pre_samples * c.pre_head_stride + (int64_t)c.pre_samples * 8 + c.mlp_out;
-  return (n_rays * per_ray * (int64_t)sizeof(float) + 255) / 256 * 256;
+  auto seg = [](int64_t floats) { return (floats * (int64_t)sizeof(float) + 255) / 256 * 256; };  // each buffer 256-byte aligned
+  return seg(n_rays * c.pre_samples * c.pre_head_stride) + seg(n_rays * c.pre_samples * 8) + seg(n_rays * (int64_t)c.mlp_out);
 }
 
 // workspace of one render call over n rays that is not split further
@@ -689,9 +689,10 @@ static int launch_sample_net(hr_handle* h, const float* rays, int64_t n, float* 
   if (!c.cascade) return launch_net(h, h->cfg_net, h->simt, h->tc, h->tc_ready, rays, n, heads, st);
   if (!scratch) return fail("hr_render: cascade scratch missing");
   // PointPredictionEmbedding (nlf/embedding/point.py:142-206): ray net -> S0 z-planes -> one point-net row per point
-  float* heads0 = (float*)scratch;                                                   // [n][S0*stride0] channel-major
-  float* rows = heads0 + n * (int64_t)c.pre_samples * c.pre_head_stride;             // [n*S0][8]
-  float* out = rows + n * (int64_t)c.pre_samples * 8;                                // [n*S0][mlp_out/S0] = [n][S][stride]
+  auto seg = [](int64_t floats) { return (floats * (int64_t)sizeof(float) + 255) / 256 * 256; };  // as in cascade_bytes
+  float* heads0 = (float*)scratch;                                                                // [n][S0*stride0] channel-major
+  float* rows = (float*)((char*)heads0 + seg(n * c.pre_samples * c.pre_head_stride));              // [n*S0][8]
+  float* out = (float*)((char*)rows + seg(n * c.pre_samples * 8));                                 // [n*S0][mlp_out/S0] = [n][S][stride]
   const bool has_pre = c.pre_mlp_mode != HR_MLP_ZERO;
   if (has_pre) {
     int rc = launch_net(h, h->cfg_pre, h->simt_pre, h->tc_pre, h->tc_pre_ready, rays, n, heads0, st);

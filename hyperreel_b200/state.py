@@ -88,6 +88,23 @@ class _Tensorf(nn.Module):
         self.alphaMask = None
         self.device = "cuda"
         self.init_svd_volume(None, None)
+        # up-sampling schedule (tensorf_base.py:150-197): log-spaced voxel counts (or per-axis grid sizes) between the initial and
+        # the final grid, one step per entry of upsamp_list
+        net = sig.model_cfg.color.net
+        self.upsamp_list = [int(v) for v in (net.get("upsamp_list", []) or [])]
+        self.lr_upsample_reset = bool(net.get("lr_upsample_reset", False))
+        self.needs_opt_reset = False
+        self.cur_iter = 0
+        steps = len(self.upsamp_list) + 1
+        import math
+        if "grid_size" in net:
+            self.use_grid_size_upsample = True
+            self.N_voxel_list = [torch.round(torch.exp(torch.linspace(math.log(float(net.grid_size.start[i])), math.log(float(net.grid_size.end[i])),
+                                                                        steps))).long().tolist()[1:] for i in range(3)]
+        else:
+            self.use_grid_size_upsample = False
+            n0, n1 = float(net.get("N_voxel_init", 1)), float(net.get("N_voxel_final", net.get("N_voxel_init", 1)))
+            self.N_voxel_list = torch.round(torch.exp(torch.linspace(math.log(n0), math.log(n1), steps))).long().tolist()[1:]
 
     def _shapes(self, comps, i, grid):
         a, b = MAT_MODE[i]
@@ -120,13 +137,82 @@ class _Tensorf(nn.Module):
     def update_stepSize(self, gridSize):
         self.gridSize = torch.as_tensor(gridSize, dtype=torch.long)
 
+    # ---- grid up-sampling (tensorf_base.py:1151-1188 `up_sampling_VM` / `upsample_volume_grid`, tensorf_dynamic.py:394-441):
+    # bilinear, align_corners=True re-sampling of every table, new Parameter objects (the optimiser must be rebuilt)
+    @torch.no_grad()
+    def upsample_volume_grid(self, res_target):
+        import torch.nn.functional as F
+
+        res = [int(v) for v in res_target]
+        dp, d2, ap, a2 = self.tables()
+        for planes, seconds, comps in ((ap, a2, self.n_app), (dp, d2, self.n_sigma)):
+            for i in range(3):
+                a, b = MAT_MODE[i]
+                v = VEC_MODE[i]
+                size2 = (self.K, res[v]) if self.dynamic else (res[v], 1)
+                if planes[i].shape[1] == 0:
+                    # empty groups are re-created at the new size (the dynamic net writes zeros, :402-408; an interpolate of a
+                    # 0-channel tensor gives the same empty tensor for the static one)
+                    planes[i] = nn.Parameter(planes[i].data.new_zeros(1, comps[i], res[b], res[a]))
+                    seconds[i] = nn.Parameter(seconds[i].data.new_zeros(1, comps[i], *size2))
+                    continue
+                planes[i] = nn.Parameter(F.interpolate(planes[i].data, size=(res[b], res[a]), mode="bilinear", align_corners=True))
+                seconds[i] = nn.Parameter(F.interpolate(seconds[i].data, size=size2, mode="bilinear", align_corners=True))
+        self.update_stepSize(res)
+        self.gridSize = self.gridSize.to(dp[0].device)
+        self.struct_version = getattr(self, "struct_version", 0) + 1
+
+    # ---- regulariser terms of nlf/regularizers/tensorf.py:35-96 (tensorf_base.py:1024-1057, tensorf_dynamic.py:246-286)
+    def density_L1(self):
+        dp, d2, _, _ = self.tables()
+        total = 0
+        for i in range(3):
+            if dp[i].shape[1] == 0:
+                continue
+            total = total + torch.mean(torch.abs(dp[i])) + torch.mean(torch.abs(d2[i]))
+        return total
+
+    def TV_loss_density(self, reg):
+        dp, _, _, _ = self.tables()
+        total = 0
+        for i in range(3):
+            if dp[i].shape[1] == 0:
+                continue
+            total = total + reg(dp[i]) * 1e-2
+        return total
+
+    def TV_loss_app(self, reg):
+        dp, _, ap, _ = self.tables()
+        total = 0
+        for i in range(3):
+            if (dp[i].shape[1] if self.dynamic else ap[i].shape[1]) == 0:
+                continue
+            total = total + reg(ap[i]) * 1e-2
+        return total
+
     def tables(self):
         if self.dynamic:
             return self.density_plane_space, self.density_plane_time, self.app_plane_space, self.app_plane_time
         return self.density_plane, self.density_line, self.app_plane, self.app_line
 
     def set_iter(self, i):
+        """TensorBase.set_iter (tensorf_base.py:509-553), the up-sampling half: in training mode, at the iterations of
+        `upsamp_list`, re-sample every table to the next grid of the schedule and ask for an optimiser reset.  The alpha-mask
+        update / aabb shrink of `update_AlphaMask_list` (:517-529) is not mirrored."""
         self.cur_iter = i
+        if not self.training:
+            return
+        self.needs_opt_reset = False
+        if i in self.upsamp_list and len(self.N_voxel_list) > 0:
+            if self.use_grid_size_upsample:
+                if len(self.N_voxel_list[0]) == 0:
+                    return
+                reso = [self.N_voxel_list[k].pop(0) for k in range(3)]
+            else:
+                reso = n_to_reso(self.N_voxel_list.pop(0), self.aabb.detach().cpu())
+            self.upsample_volume_grid(reso)
+            if self.lr_upsample_reset:
+                self.needs_opt_reset = True
 
 
 class _Color(nn.Module):

@@ -5,8 +5,9 @@ Only what sits on the hot path is kept: construction from the full config (``cfg
 ``load_state_dict`` with the reference's grid-size fix-up (nlf/__init__.py:433-479), including Lightning
 checkpoints whose keys carry the ``render_fn.`` prefix, and -- SURVEY.md section 8 row f1 -- ``configure_optimizers`` /
 ``training_step`` (nlf/__init__.py:504-523, 634-709) over the differentiable path: image loss, manual optimisation with
-one Adam per optimiser group.  Regularisers, the grid up-sampling schedule, visualisers and datasets are out of scope
-(SURVEY.md section 2).
+one Adam per optimiser group, the TensoRF regulariser (L1 + TV on the tables, nlf/regularizers/tensorf.py:35-96) and the grid
+up-sampling schedule with its optimiser reset (tensorf_base.py:509-553,1151-1188).  The alpha-mask / shrink step, visualisers
+and datasets are out of scope.
 """
 from __future__ import annotations
 
@@ -18,6 +19,59 @@ from torch import nn
 from .config import Cfg, epochs_to_iters, to_cfg
 from .models import model_dict
 from .rendering import render_chunked, render_fn_dict
+
+
+class TVLoss(nn.Module):
+    """nlf/regularizers/tensorf.py:14-32: 2 * (mean squared row difference + mean squared column difference) / batch."""
+
+    def forward(self, x):
+        count_h = x[:, :, 1:, :].size(1) * x[:, :, 1:, :].size(2) * x[:, :, 1:, :].size(3)
+        count_w = x[:, :, :, 1:].size(1) * x[:, :, :, 1:].size(2) * x[:, :, :, 1:].size(3)
+        h_tv = torch.pow(x[:, :, 1:, :] - x[:, :, :-1, :], 2).sum()
+        w_tv = torch.pow(x[:, :, :, 1:] - x[:, :, :, :-1], 2).sum()
+        return 2 * (h_tv / count_h + w_tv / count_w) / x.size(0)
+
+
+class TensoRFRegularizer:
+    """The TensoRF regulariser of the reference (nlf/regularizers/tensorf.py:35-96; conf/experiment/regularizers/tensorf/
+    *.yaml): L1 on the density tables plus total variation on the space planes, the TV weights decaying by `lr_factor` per
+    use exactly like the reference (which scales the *running* weights but multiplies by the configured ones, :79-88)."""
+
+    def __init__(self, cfg):
+        import math
+
+        self.cfg = to_cfg(cfg)
+        self.tvreg = TVLoss()
+        self.cur_iter = 0
+        self.update_AlphaMask_list = list(self.cfg.get("update_AlphaMask_list", []))
+        self.lr_factor = float(self.cfg.lr_decay_target_ratio) ** (1.0 / float(self.cfg.n_iters))
+        self.total_num_tv_iters = (int(self.cfg.total_num_tv_iters) if "total_num_tv_iters" in self.cfg else
+                                   int(round(math.log(1e-4) / math.log(float(self.cfg.lr_decay_target_ratio)) * float(self.cfg.n_iters))))
+        self.L1_reg_weight = float(self.cfg.L1_weight_initial)
+        self.TV_weight_density = float(self.cfg.TV_weight_density)
+        self.TV_weight_app = float(self.cfg.TV_weight_app)
+
+    def loss(self, tensorf):
+        total = 0.0
+        if self.L1_reg_weight > 0:
+            total = total + self.L1_reg_weight * tensorf.density_L1()
+        if self.cur_iter > self.total_num_tv_iters:
+            return total
+        loss_tv = 0.0
+        if self.TV_weight_density > 0:
+            self.TV_weight_density *= self.lr_factor
+            loss_tv = tensorf.TV_loss_density(self.tvreg) * float(self.cfg.TV_weight_density)
+            total = total + loss_tv
+        if self.TV_weight_app > 0:
+            self.TV_weight_app *= self.lr_factor
+            loss_tv = loss_tv + tensorf.TV_loss_app(self.tvreg) * float(self.cfg.TV_weight_app)  # the density term is counted twice, as in :85-88
+            total = total + loss_tv
+        return total
+
+    def set_iter(self, iteration):
+        self.cur_iter = iteration
+        if len(self.update_AlphaMask_list) > 0 and self.cur_iter == self.update_AlphaMask_list[0]:
+            self.L1_reg_weight = float(self.cfg.L1_weight_rest)
 
 
 class INRSystem(nn.Module):
@@ -37,6 +91,13 @@ class INRSystem(nn.Module):
         self.rendering = False
         self.render_fn = render_fn_dict[self.cfg.model.render.type](
             model, None, self.cfg.model.render, net_chunk=training.get("net_chunk", 32768))
+        # regularisers (nlf/__init__.py:396-407): only the TensoRF one touches this path's parameters
+        self.regularizers = []
+        for key, rcfg in (self.cfg.get("regularizers", Cfg()) or Cfg()).items():
+            if rcfg.get("type") == "tensorf":
+                self.regularizers.append(TensoRFRegularizer(rcfg))
+            else:
+                raise NotImplementedError(f"regularizer '{rcfg.get('type')}' is outside the fused path's scope")
         self.eval()
 
     # ---- nlf/__init__.py:481-502
@@ -70,6 +131,7 @@ class INRSystem(nn.Module):
         training = self.cfg.get("training", Cfg())
         ocfg = training.get("optimizers", Cfg())
         self._optimizers = []
+        self._opt_struct = self.render_fn.model.color_model.net.struct_version
         for key, params in self.optimizer_groups().items():
             params = [p for p in params if p.numel() > 0]
             if not params:
@@ -81,12 +143,29 @@ class INRSystem(nn.Module):
                                                      weight_decay=float(oc.get("weight_decay", 0)), betas=(0.9, 0.99)))
         return self._optimizers
 
-    def training_step(self, batch, batch_idx: int = 0):
+    def set_train_iter(self, train_iter: int):
+        """The per-iteration hook of the reference's loop (nlf/__init__.py:592-632): the colour net's schedule (grid
+        up-sampling, tensorf_base.py:509-553) and the regularisers' (`L1_weight_rest`), then an optimiser rebuild when the
+        tables were re-created (`lr_upsample_reset`, nlf/__init__.py:541-578 -- here every group restarts, Adam state of the old
+        Parameter objects is meaningless for the new ones)."""
+        model = self.render_fn.model
+        model.color_model.set_iter(int(train_iter))
+        for reg in self.regularizers:
+            reg.set_iter(int(train_iter))
+        net = model.color_model.net
+        if getattr(net, "needs_opt_reset", False) or (getattr(self, "_opt_struct", None) not in (None, net.struct_version)):
+            self.configure_optimizers()
+            net.needs_opt_reset = False
+
+    def training_step(self, batch, batch_idx: int = 0, train_iter: Optional[int] = None):
         """One iteration of nlf/__init__.py:634-709 on this path: batch {'coords' [N,C], 'rgb' [N,3], optional 'weight'};
-        loss = MSE(rgb_pred * w, rgb * w) (losses.py 'mse'), manual optimisation (zero_grad / backward / step per group)."""
+        loss = MSE(rgb_pred * w, rgb * w) (losses.py 'mse') + regularisers, manual optimisation (zero_grad / backward / step
+        per group).  `train_iter` (optional) drives the schedules like the reference's `set_train_iter`."""
+        self.train()
+        if train_iter is not None:
+            self.set_train_iter(train_iter)
         if not getattr(self, "_optimizers", None):
             self.configure_optimizers()
-        self.train()
         coords, rgb = batch["coords"], batch["rgb"]
         weight = batch.get("weight", None)
         results = self(coords)
@@ -95,6 +174,8 @@ class INRSystem(nn.Module):
             loss = torch.mean((pred * weight - rgb * weight) ** 2)
         else:
             loss = torch.mean((pred - rgb) ** 2)
+        for reg in self.regularizers:  # nlf/__init__.py:677-683 (loss weight 1: `exponential_decay` with decay 1.0)
+            loss = loss + reg.loss(self.render_fn.model.color_model.net)
         for opt in self._optimizers:
             opt.zero_grad(set_to_none=True)
         loss.backward()

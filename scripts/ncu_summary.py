@@ -9,6 +9,7 @@ import sys
 
 rep, tag = sys.argv[1], sys.argv[2]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles")  # on the GPU box: gpurun_out (the only directory copied back)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
@@ -48,8 +49,8 @@ for r in rows[2:]:
               "l1_wavefront_pct": float(vals["l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"][0]),
               "warps_active_pct": float(vals["sm__warps_active.avg.pct_of_peak_sustained_active"][0]),
               "note": "65536 rays x 32 samples, L2 flushed before the step"}
-        with open(os.path.join(ROOT, "profiles", "render_kernel_traffic.json"), "w") as f:
+        with open(os.path.join(OUT, "render_kernel_traffic.json" if tag.count("_") == 0 else f"{tag}_traffic.json"), "w") as f:
             json.dump(js, f, indent=1)
-with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w") as f:
+with open(os.path.join(OUT, f"{tag}_ncu_summary.md"), "w") as f:
     f.write("\n".join(out) + "\n")
 print("wrote", f"profiles/{tag}_ncu_summary.md")

@@ -136,3 +136,38 @@ def test_system_training_step_mirrors_the_reference_loop():
     sd = {k[len("render_fn."):]: v.detach().cpu() for k, v in system.state_dict().items()}
     ref = HyperReelOracle(case.model_cfg_plain, case.dataset, sd).render(case.rays.clone())
     assert float((a - ref).abs().max()) <= 1e-4
+
+
+def test_training_across_a_grid_upsampling_step_with_the_tensorf_regulariser():
+    """The schedule half of the reference's loop: `set_train_iter` re-samples the tables at an `upsamp_list` iteration
+    (tensorf_base.py:509-553,1151-1188), the optimisers restart on the new Parameter objects, the TensoRF regulariser
+    (nlf/regularizers/tensorf.py:35-96) adds its L1 / TV terms, training continues on the fused kernels at the new grid, and the
+    re-packed model renders what the oracle computes from the up-sampled parameters."""
+    case = build_case("donerf_app", n=1024)
+    mcfg = hb.to_cfg(hb.config.to_plain(case.model_cfg))
+    mcfg.color.net.N_voxel_init, mcfg.color.net.N_voxel_final = 40 ** 3, 56 ** 3
+    mcfg.color.net.upsamp_list, mcfg.color.net.lr_upsample_reset = [3], True
+    reg = {"type": "tensorf", "update_AlphaMask_list": [], "lr_decay_target_ratio": 0.1, "n_iters": 30000,
+           "L1_weight_initial": 8e-5, "L1_weight_rest": 4e-5, "TV_weight_density": 0.05, "TV_weight_app": 0.05}
+    cfg = hb.to_cfg({"model": mcfg, "training": {"ray_chunk": 1 << 20, "iters_per_epoch": 4000,
+                                                 "optimizers": {"color": {"lr": 0.002}, "color_impl": {"lr": 0.001},
+                                                                "embedding_impl": {"lr": 0.0002}}},
+                     "dataset": case.dataset, "regularizers": {"tensorf": reg}})
+    system = hb.INRSystem(cfg)
+    system.load_state_dict(case.state_dict)
+    system.cuda()
+    net = system.render_fn.model.color_model.net
+    grid0 = net.gridSize.tolist()
+    g = torch.Generator().manual_seed(0)
+    batch = {"coords": case.rays.cuda(), "rgb": torch.rand(case.rays.shape[0], 3, generator=g).cuda()}
+    losses = [float(system.training_step(batch, train_iter=i)["train/loss"]) for i in range(7)]
+    grid1 = net.gridSize.tolist()
+    assert grid1 != grid0 and all(b > a for a, b in zip(grid0, grid1)), (grid0, grid1)
+    assert net.density_plane[0].shape[-1] == grid1[0] and net.density_line[0].shape[2] == grid1[2]
+    assert losses[-1] < losses[0] and losses[-1] < losses[3], losses  # keeps improving after the re-sampling at iteration 3
+    system.eval()
+    with torch.no_grad():
+        a = system(case.rays.cuda())["rgb"].cpu()
+    sd = {k[len("render_fn."):]: v.detach().cpu() for k, v in system.state_dict().items()}
+    ref = HyperReelOracle(hb.config.to_plain(mcfg), case.dataset, sd).render(case.rays.clone())
+    assert float((a - ref).abs().max()) <= 1e-4
