@@ -40,28 +40,32 @@ __device__ __forceinline__ void fetch(Taps<C, ROWS2>& t, const float* __restrict
   if constexpr (C == 8 && ROWS2) t.b = ldg4(tab + off + rs);
 }
 
-// Interpolate across the quad.  C == 8: result = this lane's 4-channel half; C == 4: all 4 channels (replicated).
-template <int C, bool ROWS2>
-__device__ __forceinline__ void interp(const Taps<C, ROWS2>& t, float w0, float w1, float (&out)[4]) {
+// This lane's share of the bilinear plane interpolation (no cross-lane traffic):
+//   C == 8: its x tap, both rows, its 4-channel half;  C == 4: its (x, y) tap, all 4 channels.
+// Summing the shares over the quad (C == 8: over xt; C == 4: over xt and yt) gives the interpolated channels.
+template <int C>
+__device__ __forceinline__ void plane_share(const Taps<C, true>& t, float fa, float fb, int xt, int alt, float (&out)[4]) {
+  const float wa = xt ? fa : 1.0f - fa;
   if constexpr (C == 8) {
-    if constexpr (ROWS2) {
-      out[0] = fmaf(w1, t.b.x, w0 * t.a.x);
-      out[1] = fmaf(w1, t.b.y, w0 * t.a.y);
-      out[2] = fmaf(w1, t.b.z, w0 * t.a.z);
-      out[3] = fmaf(w1, t.b.w, w0 * t.a.w);
-    } else {
-      out[0] = w0 * t.a.x; out[1] = w0 * t.a.y; out[2] = w0 * t.a.z; out[3] = w0 * t.a.w;
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] += __shfl_xor_sync(kFull, out[c], 2);
+    const float w0 = wa * (1.0f - fb), w1 = wa * fb;
+    out[0] = fmaf(w1, t.b.x, w0 * t.a.x);
+    out[1] = fmaf(w1, t.b.y, w0 * t.a.y);
+    out[2] = fmaf(w1, t.b.z, w0 * t.a.z);
+    out[3] = fmaf(w1, t.b.w, w0 * t.a.w);
   } else {
-    out[0] = w0 * t.a.x; out[1] = w0 * t.a.y; out[2] = w0 * t.a.z; out[3] = w0 * t.a.w;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      out[c] += __shfl_xor_sync(kFull, out[c], 1);
-      out[c] += __shfl_xor_sync(kFull, out[c], 2);
-    }
+    const float w = wa * (alt ? fb : 1.0f - fb);
+    out[0] = w * t.a.x; out[1] = w * t.a.y; out[2] = w * t.a.z; out[3] = w * t.a.w;
   }
+}
+
+// The second factor (2-tap line), complete in every lane of the quad: each lane holds the tap of its xt (C == 8: its channel
+// half; C == 4: all 4 channels, the two yt lanes hold the same tap), so one exchange across xt finishes it -- 4 shuffles.
+template <int C>
+__device__ __forceinline__ void line_full(const Taps<C, false>& t, float fc, int xt, float (&out)[4]) {
+  const float wc = xt ? fc : 1.0f - fc;
+  out[0] = wc * t.a.x; out[1] = wc * t.a.y; out[2] = wc * t.a.z; out[3] = wc * t.a.w;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c] += __shfl_xor_sync(kFull, out[c], 2);
 }
 
 // One VM group (space plane x second factor) of one field for one sample.
@@ -91,22 +95,33 @@ __device__ __forceinline__ void group_fetch(GroupTaps<C, DYN>& g, const PlaneTab
   fetch<C, false>(g.se, T.second, eo, 0);
 }
 
-// -> prod[4] = space_c * second_c for this lane's channels (C==8: own half; C==4: all, replicated)
+// Density feature of one group: sum_c plane_c * line_c.  The plane stays in per-lane shares: the products with the complete
+// line are summed per lane and only the scalar crosses the quad (2 shuffles instead of 4 + 1 for C == 8, 8 for C == 4).
 template <int C, bool DYN>
-__device__ __forceinline__ void group_products(const GroupTaps<C, DYN>& g, float fa, float fb, float fc, int xt, int alt,
-                                               float (&prod)[4]) {
-  const float wa = xt ? fa : 1.0f - fa;
-  const float wc = xt ? fc : 1.0f - fc;
-  float A[4], B[4];
-  if constexpr (C == 8) {
-    interp<C, true>(g.sp, wa * (1.0f - fb), wa * fb, A);
-    interp<C, false>(g.se, wc, 0.0f, B);
-  } else {
-    interp<C, true>(g.sp, wa * (alt ? fb : 1.0f - fb), 0.0f, A);
-    interp<C, false>(g.se, alt ? 0.0f : wc, 0.0f, B);
-  }
+__device__ __forceinline__ float group_sigma(const GroupTaps<C, DYN>& g, float fa, float fb, float fc, int xt, int alt) {
+  float P[4], L[4];
+  plane_share<C>(g.sp, fa, fb, xt, alt, P);
+  line_full<C>(g.se, fc, xt, L);
+  float s = (P[0] * L[0] + P[1] * L[1]) + (P[2] * L[2] + P[3] * L[3]);
+  s += __shfl_xor_sync(kFull, s, 2);
+  s += __shfl_xor_sync(kFull, s, 1);
+  return s;
+}
+
+// Appearance features of one group: prod[4] = plane_c * line_c for this lane's channels (C == 8: own half; C == 4: all four,
+// replicated in the quad).
+template <int C, bool DYN>
+__device__ __forceinline__ void group_app(const GroupTaps<C, DYN>& g, float fa, float fb, float fc, int xt, int alt,
+                                          float (&prod)[4]) {
+  float P[4], L[4];
+  plane_share<C>(g.sp, fa, fb, xt, alt, P);
+  line_full<C>(g.se, fc, xt, L);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) prod[c] = A[c] * B[c];
+  for (int c = 0; c < 4; ++c) {
+    P[c] += __shfl_xor_sync(kFull, P[c], 2);
+    if constexpr (C == 4) P[c] += __shfl_xor_sync(kFull, P[c], 1);
+    prod[c] = P[c] * L[c];
+  }
 }
 
 template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool EXTRA, int RPW, bool RARE>
@@ -391,10 +406,14 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       if ((RPW == 1 ? rd : (rd % (LW / 8))) * 8 >= S) continue;  // warp-uniform
       const int j = rd >> 2;
       const int src = (rd & 3) * 8 + quad;
-      const int krow_s = (RPW == 1) ? krow : __shfl_sync(kFull, krow, src);
-      int sx = __shfl_sync(kFull, ix[j], src);
-      const int sy = __shfl_sync(kFull, iy[j], src);
-      const int sz = __shfl_sync(kFull, iz[j], src);
+      // texel indices travel packed (grids have < 65535 texels per axis; an invalid sample carries ix = 0xffff)
+      const unsigned pxy = __shfl_sync(kFull, (unsigned)(ix[j] & 0xffff) | ((unsigned)iy[j] << 16), src);
+      const unsigned pzk = __shfl_sync(kFull, (unsigned)iz[j] | ((unsigned)krow << 16), src);
+      const int krow_s = (RPW == 1) ? krow : (int)(pzk >> 16);
+      int sx = (int)(pxy & 0xffffu);
+      if (sx == 0xffff) sx = -1;
+      const int sy = (int)(pxy >> 16);
+      const int sz = (int)(pzk & 0xffffu);
       const float gx = __shfl_sync(kFull, fx[j], src);
       const float gy = __shfl_sync(kFull, fy[j], src);
       const float gz = __shfl_sync(kFull, fz[j], src);
@@ -413,15 +432,13 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         group_fetch<C2, DYN>(s2, tabs.sig[2], sy, sz, sx, krow_s, xt, alt, ok);
         group_fetch<C2, DYN>(a2, tabs.app[2], sy, sz, sx, krow_s, xt, alt, ok);
       }
-      // density feature: sum_c space_c * second_c over all groups (tensorf_dynamic.py:330, tensorf_no_sample.py:76-78)
+      // density feature: sum_c space_c * second_c over all groups (tensorf_dynamic.py:330, tensorf_no_sample.py:76-78);
+      // appearance features f[NT] in this lane's column order (fcol)
       float f[NT];
-      float sf;
+      float sf = group_sigma<C0, DYN>(s0, gx, gy, gz, xt, alt);
       {
         float p[4];
-        group_products<C0, DYN>(s0, gx, gy, gz, xt, alt, p);
-        sf = (p[0] + p[1]) + (p[2] + p[3]);
-        if constexpr (C0 == 8) sf += __shfl_xor_sync(kFull, sf, 1);
-        group_products<C0, DYN>(a0, gx, gy, gz, xt, alt, p);
+        group_app<C0, DYN>(a0, gx, gy, gz, xt, alt, p);
 #pragma unroll
         for (int c = 0; c < 4; ++c) f[c] = p[c];
         if constexpr (C0 == 8) {
@@ -431,11 +448,8 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       }
       if constexpr (C1 > 0) {
         float p[4];
-        group_products<C1, DYN>(s1, gx, gz, gy, xt, alt, p);
-        float part = (p[0] + p[1]) + (p[2] + p[3]);
-        if constexpr (C1 == 8) part += __shfl_xor_sync(kFull, part, 1);
-        sf += part;
-        group_products<C1, DYN>(a1, gx, gz, gy, xt, alt, p);
+        sf += group_sigma<C1, DYN>(s1, gx, gz, gy, xt, alt);
+        group_app<C1, DYN>(a1, gx, gz, gy, xt, alt, p);
 #pragma unroll
         for (int c = 0; c < 4; ++c) f[C0 + c] = p[c];
         if constexpr (C1 == 8) {
@@ -445,11 +459,8 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       }
       if constexpr (C2 > 0) {
         float p[4];
-        group_products<C2, DYN>(s2, gy, gz, gx, xt, alt, p);
-        float part = (p[0] + p[1]) + (p[2] + p[3]);
-        if constexpr (C2 == 8) part += __shfl_xor_sync(kFull, part, 1);
-        sf += part;
-        group_products<C2, DYN>(a2, gy, gz, gx, xt, alt, p);
+        sf += group_sigma<C2, DYN>(s2, gy, gz, gx, xt, alt);
+        group_app<C2, DYN>(a2, gy, gz, gx, xt, alt, p);
 #pragma unroll
         for (int c = 0; c < 4; ++c) f[C0 + C1 + c] = p[c];
         if constexpr (C2 == 8) {
