@@ -338,7 +338,20 @@ render_bwd_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__
         offv[j][c] = cfg.use_offset ? apply_act(cfg.offset_act, apply_act(cfg.act_offset, ho)) : 0.0f;
       }
     }
-    if (cfg.isect_sort) sort_pairs<SPL>(tkey, tid, lane);
+    if (cfg.isect_sort) {
+      // keys already in order (the usual case for a trained model): the (key, id) network would return the identity
+      bool bad = false;
+#pragma unroll
+      for (int r = 0; r < SPL; ++r) {
+        float prev = __shfl_up_sync(kFull, tkey[r], 1);
+        if (r > 0) {
+          const float last = __shfl_sync(kFull, tkey[r > 0 ? r - 1 : 0], 31);
+          if (lane == 0) prev = last;
+        }
+        bad = bad || (((r > 0) || (lane > 0)) && (prev > tkey[r]));
+      }
+      if (__any_sync(kFull, bad)) sort_pairs<SPL>(tkey, tid, lane);
+    }
 
     // ---- points, validity, texel coordinates (position e = lane + 32 j in sorted order) ----
     float dist[SPL], fx[SPL], fy[SPL], fz[SPL], praw[SPL][3];

@@ -124,6 +124,42 @@ __device__ __forceinline__ void group_app(const GroupTaps<C, DYN>& g, float fa, 
   }
 }
 
+// One VM group's contribution to this lane's four partial sums v = (colour 0, colour 1, colour 2, density feature):
+//   density    v[3] += sum_c plane_c * line_c                    (tensorf_dynamic.py:330, tensorf_no_sample.py:76-78)
+//   appearance v[q] += sum_c G[q][c] * plane_c * line_c           (basis_mat + shading folded into G, :371 / tensorf_utils.py:334-343)
+// The plane factors stay per-lane shares (this lane's taps only) and the line factors are completed with one exchange each, so
+// the products are partial sums over the quad: nothing but the two line exchanges (4 shuffles each) crosses lanes here; the
+// four scalars of ALL groups are reduced once per sample by quad_transpose_reduce.
+template <int C, bool DYN>
+__device__ __forceinline__ void group_accumulate(const GroupTaps<C, DYN>& sg, const GroupTaps<C, DYN>& ag, float fa, float fb,
+                                                 float fc, int xt, int alt, const float* __restrict__ G0,
+                                                 const float* __restrict__ G1, const float* __restrict__ G2, float (&v)[4]) {
+  float P[4], L[4];
+  plane_share<C>(sg.sp, fa, fb, xt, alt, P);
+  line_full<C>(sg.se, fc, xt, L);
+  v[3] += (P[0] * L[0] + P[1] * L[1]) + (P[2] * L[2] + P[3] * L[3]);
+  plane_share<C>(ag.sp, fa, fb, xt, alt, P);
+  line_full<C>(ag.se, fc, xt, L);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float t = P[c] * L[c];
+    v[0] = fmaf(G0[c], t, v[0]);
+    v[1] = fmaf(G1[c], t, v[1]);
+    v[2] = fmaf(G2[c], t, v[2]);
+  }
+}
+
+// Sum v[0..3] over the 4 lanes of a quad so that lane q ends up with the total of v[q] (a transposing butterfly: 3 shuffles
+// instead of the 8 of four replicated all-reduces).  Lane q = (xt << 1) | alt.
+__device__ __forceinline__ float quad_transpose_reduce(const float (&v)[4], int xt, int alt) {
+  const float x = __shfl_xor_sync(kFull, xt ? v[0] : v[2], 2);
+  const float y = __shfl_xor_sync(kFull, xt ? v[1] : v[3], 2);
+  const float k0 = (xt ? v[2] : v[0]) + x;  // xt = 0 keeps (v0, v1), xt = 1 keeps (v2, v3)
+  const float k1 = (xt ? v[3] : v[1]) + y;
+  const float z = __shfl_xor_sync(kFull, alt ? k0 : k1, 1);
+  return (alt ? k1 : k0) + z;                // q = 0: v0, 1: v1, 2: v2, 3: v3
+}
+
 template <int SPL, bool DYN, int C0, int C1, int C2, int SHADE, bool EXTRA, int RPW, bool RARE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, SPL > 2 ? 1 : ((C1 + C2 == 0 || SPL == 1) ? 3 : 2))
 render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Derived dv,
@@ -148,29 +184,42 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
   const long long warp0 = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
 
-  // Column of basis_mat feeding this lane's i-th product feature.  For an 8-channel group the lane holds
-  // [own half | other half]; 4-channel groups are replicated in natural order.
-  int fcol[NT];
+  // This lane's channel slots: an 8-channel group contributes its 4-channel half (`alt`), a 4-channel group all four.
+  // lcol[i] = column of basis_mat of slot i;  G[r][q][i] = entry (colour q, slot i) of the view-folded appearance matrix of
+  // ray r of the warp: every lane carries all three colours of its slots (the colour sums are reduced across the quad).
+  constexpr int N0 = (C0 == 8) ? 4 : C0, N1 = (C1 == 8) ? 4 : C1, N2 = (C2 == 8) ? 4 : C2;
+  constexpr int NTL = N0 + N1 + N2;
+  int lcol[NTL];
 #pragma unroll
-  for (int i = 0; i < NT; ++i) fcol[i] = i;
-  if constexpr (C0 == 8) {
+  for (int i = 0; i < N0; ++i) lcol[i] = ((C0 == 8) ? alt * 4 : 0) + i;
+#pragma unroll
+  for (int i = 0; i < N1; ++i) lcol[N0 + i] = C0 + ((C1 == 8) ? alt * 4 : 0) + i;
+#pragma unroll
+  for (int i = 0; i < N2; ++i) lcol[N0 + N1 + i] = C0 + C1 + ((C2 == 8) ? alt * 4 : 0) + i;
+  // Two ways to finish a sample (measured, profiles/r2_notes.md):
+  //   FOLD  (several groups, [8,4,4] / [8,8,8]): every lane accumulates partial sums of all three colours and of the density
+  //         over its own taps / channels (G = all three colour rows of its slots), one transposing reduction per sample;
+  //   !FOLD (one group, [8,0,0]): complete features f[NT] in every lane, each lane computes its own colour (G = one row).
+  constexpr bool FOLD = (C1 + C2) > 0;
+  constexpr int NG = (SHADE == HR_SHADE_SH) ? RPW : 1;
+  float G[FOLD ? NG : 1][FOLD ? 3 : 1][FOLD ? NTL : 1];
+  float Gr[FOLD ? 1 : NG][FOLD ? 1 : NT];
+  // !FOLD: column of basis_mat feeding this lane's i-th product feature ([own half | other half] of the 8-channel group)
+  int fcol[FOLD ? 1 : NT];
+  if constexpr (!FOLD) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { fcol[i] = alt * 4 + i; fcol[4 + i] = (1 - alt) * 4 + i; }
   }
-  if constexpr (C1 == 8) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { fcol[C0 + i] = C0 + alt * 4 + i; fcol[C0 + 4 + i] = C0 + (1 - alt) * 4 + i; }
-  }
-  if constexpr (C2 == 8) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { fcol[C0 + C1 + i] = C0 + C1 + alt * 4 + i; fcol[C0 + C1 + 4 + i] = C0 + C1 + (1 - alt) * 4 + i; }
-  }
-  // per-lane row of the (view-folded) appearance matrix of each ray of the warp: rgb_q = act(sum_i G[r][i] * f[i])
-  constexpr int NG = (SHADE == HR_SHADE_SH) ? RPW : 1;
-  float G[NG][NT];
   if constexpr (SHADE == HR_SHADE_RGB) {
+    if constexpr (FOLD) {
 #pragma unroll
-    for (int i = 0; i < NT; ++i) G[0][i] = s_basis[qc * NT + fcol[i]];
+      for (int qq = 0; qq < 3; ++qq)
+#pragma unroll
+        for (int i = 0; i < NTL; ++i) G[0][qq][i] = s_basis[qq * NT + lcol[i]];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NT; ++i) Gr[0][i] = s_basis[qc * NT + fcol[i]];
+    }
   }
 
   const float inv_x = __fdiv_rn(2.0f, __fsub_rn(cfg.aabb[3], cfg.aabb[0]));  // invaabbSize (tensorf_base.py:292)
@@ -243,19 +292,35 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         for (int k = 0; k < 9; ++k) a = fmaf(Y[k], s_basis[(eq * 9 + k) * NT + ei], a);
         g[m] = a;
       }
+      if constexpr (!FOLD) {
 #pragma unroll
-      for (int i = 0; i < NT; ++i) {
-        const int E = qc * NT + fcol[i];
+        for (int i = 0; i < NT; ++i) {
+          const int E = qc * NT + fcol[i];
 #pragma unroll
-        for (int rr = 0; rr < RPW; ++rr) {
-          float v = 0.0f;
+          for (int rr = 0; rr < RPW; ++rr) {
+            float v = 0.0f;
 #pragma unroll
-          for (int m = 0; m < GM; ++m) {
-            const float t = __shfl_sync(kFull, g[m], rr * LW + (E % LW));
-            if ((E / LW) == m) v = t;
+            for (int m = 0; m < GM; ++m) {
+              const float t = __shfl_sync(kFull, g[m], rr * LW + (E % LW));
+              if ((E / LW) == m) v = t;
+            }
+            Gr[rr][i] = v;
           }
-          G[rr][i] = v;
         }
+      } else {
+#pragma unroll
+      for (int qq = 0; qq < 3; ++qq) {
+#pragma unroll
+        for (int i = 0; i < NTL; ++i) {
+          const int E = qq * NT + lcol[i];
+          // the register holding entry E is the same for both channel halves: 8-channel blocks start at multiples of 8,
+          // 4-channel blocks at multiples of 4, and LW is a multiple of 8
+          const int blk = (i < N0) ? 0 : ((i < N0 + N1) ? C0 : C0 + C1);
+          const int m = (qq * NT + blk + ((i < N0) ? i : ((i < N0 + N1) ? i - N0 : i - N0 - N1))) / LW;
+#pragma unroll
+          for (int rr = 0; rr < RPW; ++rr) G[rr][qq][i] = __shfl_sync(kFull, g[m < GM ? m : 0], rr * LW + (E % LW));
+        }
+      }
       }
     }
 
@@ -332,8 +397,23 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
 
     // ---- sort distances only (base.py:206-210) ----
     if (cfg.isect_sort) {
-      if constexpr (RPW == 1) sort_keys<SPL>(tkey, lane);
-      else sort_keys_sub<LW>(tkey[0], sl);
+      // the keys of a trained model are usually in order already (small offsets around increasing base primitives, masked
+      // samples at t = 0 in front): one neighbour exchange + vote decides whether the 15-stage network is needed at all
+      bool bad = false;  // element e = r*32 + lane (one ray per warp) or lane within the ray's 16 (two rays per warp)
+#pragma unroll
+      for (int r = 0; r < SPL; ++r) {
+        float prev = __shfl_up_sync(kFull, tkey[r], 1);
+        if (r > 0) {
+          const float last = __shfl_sync(kFull, tkey[r > 0 ? r - 1 : 0], 31);
+          if (lane == 0) prev = last;
+        }
+        bad = bad || (((r > 0) || (sl > 0)) && (prev > tkey[r]));
+      }
+      const bool unsorted = __any_sync(kFull, bad);
+      if (unsorted) {
+        if constexpr (RPW == 1) sort_keys<SPL>(tkey, lane);
+        else sort_keys_sub<LW>(tkey[0], sl);
+      }
     }
 
     // ---- points, contraction, flow, offset, validity, texel coordinates along the three grid axes ----
@@ -396,7 +476,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
     }
 
     // ---- VM gather: 8 samples per round, 4 lanes per sample (matMode [[0,1],[0,2],[1,2]], vecMode [2,1,0]) ----
-    float sig_r[ROUNDS];  // density feature of (round, quad), replicated in the quad
+    float sig_r[ROUNDS];  // density feature of (round, quad): FOLD: in lane q = 3 of the quad, else replicated
     float rgb_r[ROUNDS];  // shaded colour channel q of (round, quad)
 #pragma unroll
     for (int rd = 0; rd < ROUNDS; ++rd) {
@@ -432,50 +512,67 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
         group_fetch<C2, DYN>(s2, tabs.sig[2], sy, sz, sx, krow_s, xt, alt, ok);
         group_fetch<C2, DYN>(a2, tabs.app[2], sy, sz, sx, krow_s, xt, alt, ok);
       }
-      // density feature: sum_c space_c * second_c over all groups (tensorf_dynamic.py:330, tensorf_no_sample.py:76-78);
-      // appearance features f[NT] in this lane's column order (fcol)
-      float f[NT];
-      float sf = group_sigma<C0, DYN>(s0, gx, gy, gz, xt, alt);
-      {
-        float p[4];
-        group_app<C0, DYN>(a0, gx, gy, gz, xt, alt, p);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) f[c] = p[c];
-        if constexpr (C0 == 8) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) f[4 + c] = __shfl_xor_sync(kFull, p[c], 1);
-        }
-      }
-      if constexpr (C1 > 0) {
-        float p[4];
-        sf += group_sigma<C1, DYN>(s1, gx, gz, gy, xt, alt);
-        group_app<C1, DYN>(a1, gx, gz, gy, xt, alt, p);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) f[C0 + c] = p[c];
-        if constexpr (C1 == 8) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) f[C0 + 4 + c] = __shfl_xor_sync(kFull, p[c], 1);
-        }
-      }
-      if constexpr (C2 > 0) {
-        float p[4];
-        sf += group_sigma<C2, DYN>(s2, gy, gz, gx, xt, alt);
-        group_app<C2, DYN>(a2, gy, gz, gx, xt, alt, p);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) f[C0 + C1 + c] = p[c];
-        if constexpr (C2 == 8) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) f[C0 + C1 + 4 + c] = __shfl_xor_sync(kFull, p[c], 1);
-        }
-      }
-      sig_r[rd] = ok ? sf : 0.0f;
-      // appearance: basis_mat (tensorf_dynamic.py:371) folded with the shading (tensorf_utils.py:334-343)
-      float acc = 0.0f;
-#pragma unroll
-      for (int i = 0; i < NT; ++i) acc = fmaf(G[(NG == 1) ? 0 : rd / (LW / 8)][i], f[i], acc);
       float col;
-      if constexpr (SHADE == HR_SHADE_SH) col = fmaxf(acc + 0.5f, 0.0f);
-      else col = 1.0f / (1.0f + expf(-acc));
+      if constexpr (FOLD) {
+        // four partial sums per lane (colours 0-2, density feature) over all groups, then one transposing reduction over the
+        // quad: lane q < 3 receives colour q, lane q = 3 the density feature
+        float v4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const int gr = (NG == 1) ? 0 : rd / (LW / 8);
+        group_accumulate<C0, DYN>(s0, a0, gx, gy, gz, xt, alt, &G[gr][0][0], &G[gr][1][0], &G[gr][2][0], v4);
+        if constexpr (C1 > 0)
+          group_accumulate<C1, DYN>(s1, a1, gx, gz, gy, xt, alt, &G[gr][0][N0], &G[gr][1][N0], &G[gr][2][N0], v4);
+        if constexpr (C2 > 0)
+          group_accumulate<C2, DYN>(s2, a2, gy, gz, gx, xt, alt, &G[gr][0][N0 + N1], &G[gr][1][N0 + N1], &G[gr][2][N0 + N1], v4);
+        const float acc = quad_transpose_reduce(v4, xt, alt);
+        sig_r[rd] = ok ? acc : 0.0f;  // meaningful in lane q = 3
+        // appearance: basis_mat (tensorf_dynamic.py:371) folded with the shading (tensorf_utils.py:334-343); lanes q < 3
+        if constexpr (SHADE == HR_SHADE_SH) col = fmaxf(acc + 0.5f, 0.0f);
+        else col = 1.0f / (1.0f + expf(-acc));
+      } else {
+        // density feature: sum_c space_c * second_c over all groups (tensorf_dynamic.py:330, tensorf_no_sample.py:76-78);
+        // appearance features f[NT] in this lane's column order (fcol)
+        float f[NT];
+        float sf = group_sigma<C0, DYN>(s0, gx, gy, gz, xt, alt);
+        {
+          float p[4];
+          group_app<C0, DYN>(a0, gx, gy, gz, xt, alt, p);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) f[c] = p[c];
+          if constexpr (C0 == 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) f[4 + c] = __shfl_xor_sync(kFull, p[c], 1);
+          }
+        }
+        if constexpr (C1 > 0) {
+          float p[4];
+          sf += group_sigma<C1, DYN>(s1, gx, gz, gy, xt, alt);
+          group_app<C1, DYN>(a1, gx, gz, gy, xt, alt, p);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) f[C0 + c] = p[c];
+          if constexpr (C1 == 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) f[C0 + 4 + c] = __shfl_xor_sync(kFull, p[c], 1);
+          }
+        }
+        if constexpr (C2 > 0) {
+          float p[4];
+          sf += group_sigma<C2, DYN>(s2, gy, gz, gx, xt, alt);
+          group_app<C2, DYN>(a2, gy, gz, gx, xt, alt, p);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) f[C0 + C1 + c] = p[c];
+          if constexpr (C2 == 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) f[C0 + C1 + 4 + c] = __shfl_xor_sync(kFull, p[c], 1);
+          }
+        }
+        sig_r[rd] = ok ? sf : 0.0f;
+        // appearance: basis_mat (tensorf_dynamic.py:371) folded with the shading (tensorf_utils.py:334-343)
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) acc = fmaf(Gr[(NG == 1) ? 0 : rd / (LW / 8)][i], f[i], acc);
+        if constexpr (SHADE == HR_SHADE_SH) col = fmaxf(acc + 0.5f, 0.0f);
+        else col = 1.0f / (1.0f + expf(-acc));
+      }
       rgb_r[rd] = ok ? col : 0.0f;
     }
 
@@ -499,7 +596,7 @@ render_kernel(const __grid_constant__ hr_config cfg, const __grid_constant__ Der
       float feat = 0.0f;
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
-        float v = __shfl_sync(kFull, sig_r[4 * j + rr], 4 * (lane & 7));
+        float v = __shfl_sync(kFull, sig_r[4 * j + rr], 4 * (lane & 7) + (FOLD ? 3 : 0));
         if ((lane >> 3) == rr) feat = v;
       }
       // feature2density (tensorf_dynamic.py:373-392; static tensorf_no_sample.py:82-88,187: weights == 1)
