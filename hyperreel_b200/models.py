@@ -508,7 +508,13 @@ class LightfieldModel(nn.Module):
             P.color_embedding = dptr(self.embedding_model.embeddings[self.sig.color_embedding_index].color_embedding)
         stream = torch.cuda.current_stream(torch.device("cuda", idx))
         L.check(self._lib.hr_upload(self._handle, C.byref(P), stream.cuda_stream))
-        stream.synchronize()
+        if self.training:
+            # a training step re-packs after every optimiser step and runs on one stream: the pack kernels are ordered before
+            # the kernels that read them, and the caching allocator releases `keep` in stream order -- no host sync, so the
+            # CPU keeps queueing the step while the GPU works
+            self._upload_keep = keep
+        else:
+            stream.synchronize()  # renders may come from any stream afterwards
         self._uploaded_version = ver
 
     def __del__(self):
