@@ -557,7 +557,8 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n * sig.c_in * 4, "d2h_bytes_per_step": n * 12,
                     "ms_per_step": float(t2.item()),
                     "path": "hr_render_host per rank: pinned rays read zero-copy over PCIe by the sample net's encoder warps (the H2D "
-                            "transfer, inside the timed region), rgb copied back D2H in two pieces; wall clock per call"},
+                            "transfer, inside the timed region), rgb stored by the render kernel's epilogue straight into the pinned "
+                            "host buffer (the D2H transfer, posted writes over PCIe); wall clock per call incl. the final sync"},
             "gpu_launches": int(launches),
             "clocks": dict(sampler.summary(), remeasured=remeasured),
             "roofline": roofline_object(sig, n, tm, peak, peak_src, ncu_summary()),

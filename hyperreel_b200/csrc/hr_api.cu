@@ -919,6 +919,14 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
       cudaGetLastError();  // pageable memory: not an error, just not device-addressable
   }
   const bool zero_copy = rays_dev_view != nullptr;
+  float* rgb_dev_view = nullptr;
+  if (zero_copy) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, rgb_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr)
+      rgb_dev_view = (float*)pa.devicePointer;
+    else
+      cudaGetLastError();
+  }
   const bool split = !zero_copy && whole && n_rays > wave;
   if (chunk <= 0) chunk = (c.mlp_mode == HR_MLP_BF16X3_TC) ? wave : 32768;
   if (chunk > n_rays) chunk = n_rays;
@@ -1009,6 +1017,15 @@ int hr_render_host(hr_handle* h, const float* rays_host, int64_t n_rays, float* 
     cudaError_t e = hr::launch_mlp_tc2(c, h->tc, h->tma_encode, rays_dev_view, heads, n_rays, h->num_sms, s0, d_rays);
     if (e != cudaSuccess) return fail("sample-net launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
+    if (rgb_dev_view != nullptr) {
+      // Zero-copy output: the caller's rgb buffer is device-addressable pinned memory too -- the render kernel's epilogue
+      // stores the pixels straight into it (12 bytes per ray as posted writes over PCIe, spread over the kernel's whole run),
+      // so there is no D2H copy and no reason to split the launch.  Completion of the stream makes the writes visible.
+      e = hr::launch_render(c, h->dv, h->tabs, d_rays, heads, one_dst(rgb_dev_view), n_rays, nullptr, h->num_sms, s0, nullptr);
+      if (e != cudaSuccess) return fail("render launch failed: %s", cudaGetErrorString(e));
+      h->launches += 1;
+      return 0;
+    }
     const int pieces = 2;
     const int64_t per = ((n_rays + pieces - 1) / pieces + 255) / 256 * 256;
     int j = 0;
