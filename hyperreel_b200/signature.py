@@ -3,8 +3,12 @@
 The reference builds an arbitrary graph from the YAML (ordered embeddings over a dict of named
 per-sample fields).  The fused CUDA path implements one family of graphs:
 
-    ray_prediction -> ray_intersect(z_plane | sphere) -> [advect_points] -> [point_offset]
-                   -> add_point_outputs -> extract_fields -> tensor_vm_split_time | tensor_vm_split_no_sample
+    ray_prediction -> ray_intersect -> [point_prediction -> ray_intersect] -> [color_transform] -> [advect_points]
+                   -> [point_offset] -> add_point_outputs -> extract_fields
+                   -> tensor_vm_split_time | tensor_vm_split_no_sample
+
+with the primitives z_plane, sphere, cylinder, sphere_new, euclidean_distance_unified, voxel_grid, deformable_voxel_grid
+(z_plane only in the first stage of a cascade), up to 256 samples per ray, `base` or `zero` sample nets.
 
 Anything else raises ``UnsupportedPipeline`` at construction -- there is no fallback path.
 Host-side constants are computed with the same torch ops the reference's constructors use
