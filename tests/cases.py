@@ -49,6 +49,9 @@ CASES: Dict[str, dict] = {
     "donerf_app": dict(builtin="donerf_sphere", over=dict(n_voxels=40 ** 3), n=256, seed=23, gain=100.0, app_gain=10.0),
     "technicolor_zero_net": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, variant="zero_net"), n=128, seed=24, gain=600.0, app_gain=6.0),
     "donerf_distance": dict(builtin="donerf_sphere", over=dict(n_voxels=32 ** 3, variant="distance"), n=192, seed=25, gain=100.0, app_gain=6.0),
+    # two rays per warp (S <= 16) with several VM groups and SH shading: per-ray folded appearance matrices for both rays of a warp
+    "neural3d_s16": dict(builtin="neural_3d_z_plane", over=dict(n_voxels=32 ** 3, z_channels=16), n=161, seed=26, gain=100.0, app_gain=6.0),
+    "technicolor_s8": dict(builtin="technicolor_z_plane", over=dict(n_voxels=32 ** 3, z_channels=8), n=131, seed=27, gain=600.0, app_gain=6.0),
     "immersive_sphere_like": dict(builtin="neural_3d_z_plane", over=dict(n_voxels=32 ** 3, z_channels=32, variant=["sphere", "outward_facing"]), n=160, seed=14, gain=30.0),
 }
 
