@@ -110,7 +110,9 @@ def test_host_buffer_entry_point_matches_device_path():
 
 def test_host_entry_point_whole_batch_pipelines_match_device_path():
     """Default chunking with the tensor-core net (hr_render_host keeps the batch whole on the device):
-    pinned rays  -> zero-copy input (the sample net's encoder warps read host memory, render in two pieces);
+    pinned rays + pinned rgb -> zero-copy input (the sample net's encoder warps read host memory) and zero-copy output (the
+                                render epilogue stores into the host buffer, one render launch, no copies);
+    pinned rays + pageable rgb -> zero-copy input, rgb copied back in two render pieces;
     pageable rays -> wave split (H2D split at the first 148 x 128-ray wave, sample net in two launches, render in four)."""
     case = build_case("technicolor_trained", n=148 * 128 + 3000)
     render = make_render(case, mlp_mode="bf16x3")
@@ -124,6 +126,11 @@ def test_host_entry_point_whole_batch_pipelines_match_device_path():
             out.zero_()
             render.model.render_host(rays, out)
             assert torch.equal(out, dev), f"pinned={pinned}"
+    mixed = torch.empty((case.rays.shape[0], 3), dtype=torch.float32)  # pageable output behind pinned input
+    for _ in range(2):
+        mixed.zero_()
+        render.model.render_host(case.rays.clone().pin_memory(), mixed)
+        assert torch.equal(mixed, dev)
     # a batch smaller than one wave through the zero-copy path
     small = case.rays[:777].clone().pin_memory()
     assert torch.equal(render.model.render_host(small), dev[:777])
