@@ -69,6 +69,21 @@ class _Embedding(nn.Module):
         self.embeddings = nn.ModuleList([entries.get(i, nn.Module()) for i in range(max(entries) + 1)])
 
 
+class _AlphaGrid:
+    """Binary occupancy volume over an aabb (the role of AlphaGridMask, utils/tensorf_utils.py:459-484): `alpha` is [Z,Y,X]."""
+
+    def __init__(self, aabb, alpha):
+        self.aabb = aabb.clone()
+        self.volume = alpha.view(1, 1, *alpha.shape[-3:])
+        self.gridSize = torch.tensor([alpha.shape[-1], alpha.shape[-2], alpha.shape[-3]], dtype=torch.long)
+
+    def sample_alpha(self, pts):
+        import torch.nn.functional as F
+
+        u = (pts - self.aabb[0]) * (1.0 / (self.aabb[1] - self.aabb[0]) * 2) - 1
+        return F.grid_sample(self.volume, u.view(1, -1, 1, 1, 3), align_corners=True).view(-1)
+
+
 class _Tensorf(nn.Module):
     """Storage twin of TensorVMKeyframeTime / TensorVMNoSample parameters (tensorf_dynamic.py:106-244,
     tensorf_base.py:895-991)."""
@@ -91,6 +106,11 @@ class _Tensorf(nn.Module):
         # up-sampling schedule (tensorf_base.py:150-197): log-spaced voxel counts (or per-axis grid sizes) between the initial and
         # the final grid, one step per entry of upsamp_list
         net = sig.model_cfg.color.net
+        self.update_AlphaMask_list = [int(v) for v in (net.get("update_AlphaMask_list", []) or [])]
+        self.alphaMask_thres = float(net.get("alpha_mask_thre", 0.001))
+        self.fea2denseAct = net.get("fea2denseAct", "softplus")
+        self.density_shift = float(net.get("density_shift", -10.0))
+        self.total_num_frames = int(c.num_frames) if c.num_frames > 0 else 1
         self.upsamp_list = [int(v) for v in (net.get("upsamp_list", []) or [])]
         self.lr_upsample_reset = bool(net.get("lr_upsample_reset", False))
         self.needs_opt_reset = False
@@ -162,6 +182,121 @@ class _Tensorf(nn.Module):
         self.gridSize = self.gridSize.to(dp[0].device)
         self.struct_version = getattr(self, "struct_version", 0) + 1
 
+    # ---- occupancy pruning: alpha-mask update and aabb shrink (tensorf_base.py:379-429,1190-1232; dynamic net
+    # tensorf_dynamic.py:443-541,618-643).  Host-side schedule steps that run once or twice per training, so they are torch ops
+    # on the reference-layout tables; the render path only ever sees their result (a smaller aabb, cropped tables): the
+    # reference disables the mask lookup in its forward (`if self.alphaMask is not None and False`, tensorf_dynamic.py:707).
+    def _density_feature(self, u, tau=None):
+        """Sum over groups and channels of space-plane x second-factor samples at normalised coordinates u [M,3] (tau [M]:
+        normalised keyframe time of the dynamic net)."""
+        import torch.nn.functional as F
+
+        dp, d2, _, _ = self.tables()
+        M = u.shape[0]
+        feat = torch.zeros((M,), device=u.device, dtype=u.dtype)
+        for i in range(3):
+            if dp[i].shape[1] == 0:
+                continue
+            a, b = MAT_MODE[i]
+            v = VEC_MODE[i]
+            plane = F.grid_sample(dp[i], torch.stack((u[:, a], u[:, b]), -1).view(1, M, 1, 2), align_corners=True).view(-1, M)
+            if self.dynamic:
+                coord = torch.stack((u[:, v], tau), -1)
+            else:
+                coord = torch.stack((torch.zeros_like(u[:, v]), u[:, v]), -1)
+            second = F.grid_sample(d2[i], coord.view(1, M, 1, 2), align_corners=True).view(-1, M)
+            feat = feat + torch.sum(plane * second, dim=0)
+        return feat
+
+    def _feature2density(self, feat):
+        import torch.nn.functional as F
+
+        if self.fea2denseAct == "softplus":
+            return F.softplus(feat + self.density_shift)
+        if self.fea2denseAct == "relu":
+            return F.relu(feat)
+        return F.relu(torch.abs(feat))
+
+    def compute_alpha(self, pts, base_times=None, length: float = 0.01):
+        """1 - exp(-sigma * length) at world points pts [M,3] (tensorf_base.py:489-507; dynamic: tensorf_dynamic.py:618-643 at
+        keyframe times base_times [M]).  The static net skips points an earlier mask marks empty."""
+        aabb = self.aabb.to(pts.device)
+        inv = 2.0 / (aabb[1] - aabb[0])
+        sigma = torch.zeros(pts.shape[0], device=pts.device, dtype=pts.dtype)
+        keep = torch.ones(pts.shape[0], dtype=torch.bool, device=pts.device)
+        if not self.dynamic and self.alphaMask is not None:
+            keep = self.alphaMask.sample_alpha(pts) > 0
+        if keep.any():
+            u = (pts[keep] - aabb[0]) * inv - 1
+            tau = None
+            if self.dynamic:
+                Fr = self.total_num_frames
+                tau = (base_times[keep] * ((Fr - 1) / Fr) + 0.5 / self.K) * 2 - 1  # normalize_time_coord (:615-616)
+            sigma[keep] = self._feature2density(self._density_feature(u, tau))
+        return 1 - torch.exp(-sigma * length)
+
+    @torch.no_grad()
+    def getDenseAlpha(self, gridSize):
+        gx, gy, gz = [int(v) for v in gridSize]
+        dev = self.tables()[0][0].device
+        aabb = self.aabb.to(dev)
+        lin = [torch.linspace(0, 1, n) for n in (gx, gy, gz)]
+        samples = torch.stack(torch.meshgrid(*lin, indexing="ij"), -1).to(dev)
+        dense_xyz = aabb[0] * (1 - samples) + aabb[1] * samples
+        flat = dense_xyz.view(-1, 3)
+        if not self.dynamic:
+            return self.compute_alpha(flat).view(gx, gy, gz), dense_xyz
+        # the dynamic net takes the maximum over all frames; a frame's keyframe time follows this function's own snap
+        # (tensorf_dynamic.py:516-521: scale (F-1)/F, not the K(F-1)/F of get_base_time)
+        alpha = torch.zeros(gx, gy, gz, device=dev)
+        Fr = self.total_num_frames
+        tsf = (Fr - 1) / Fr
+        import numpy as np
+        for t in np.linspace(0, 1, Fr):
+            times = torch.ones(flat.shape[0], device=dev) * t
+            base = torch.round((times * tsf).clamp(0.0, self.K - 1)) * (1.0 / tsf)
+            alpha = torch.maximum(alpha, self.compute_alpha(flat, base).view(gx, gy, gz))
+        return alpha, dense_xyz
+
+    @torch.no_grad()
+    def updateAlphaMask(self, gridSize=(200, 200, 200)):
+        """Dense occupancy -> 3x3x3 dilation -> threshold -> mask volume (kept as `alphaMask`) and the bounding box of the
+        occupied voxels (returned)."""
+        import torch.nn.functional as F
+
+        g = [int(v) for v in gridSize]
+        alpha, dense_xyz = self.getDenseAlpha(g)
+        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
+        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(g[::-1])
+        alpha = (alpha >= self.alphaMask_thres).to(alpha.dtype)
+        self.alphaMask = _AlphaGrid(self.aabb.to(alpha.device), alpha)
+        occupied = dense_xyz[alpha > 0.5]
+        return torch.stack((occupied.amin(0), occupied.amax(0)))
+
+    @torch.no_grad()
+    def shrink(self, new_aabb):
+        """Crop every table to the texel range covering new_aabb and move the aabb to the cropped grid's corners."""
+        dp, d2, ap, a2 = self.tables()
+        dev = dp[0].device
+        aabb, grid = self.aabb.to(dev), self.gridSize.to(dev)
+        units = (aabb[1] - aabb[0]) / (grid - 1)
+        lo = torch.round(torch.round((new_aabb[0].to(dev) - aabb[0]) / units)).long()
+        hi = torch.minimum(torch.round((new_aabb[1].to(dev) - aabb[0]) / units).long() + 1, grid)
+        for i in range(3):
+            a, b = MAT_MODE[i]
+            v = VEC_MODE[i]
+            for planes, seconds in ((dp, d2), (ap, a2)):
+                planes[i] = nn.Parameter(planes[i].data[..., lo[b]:hi[b], lo[a]:hi[a]])
+                seconds[i] = nn.Parameter(seconds[i].data[..., :, lo[v]:hi[v]] if self.dynamic else seconds[i].data[..., lo[v]:hi[v], :])
+        if self.alphaMask is None or not torch.all(self.alphaMask.gridSize.to(dev) == grid):
+            lo_r, hi_r = lo / (grid - 1), (hi - 1) / (grid - 1)
+            new_aabb = torch.stack(((1 - lo_r) * aabb[0] + lo_r * aabb[1], (1 - hi_r) * aabb[0] + hi_r * aabb[1]))
+        self.aabb = new_aabb.to(self.aabb.device).to(self.aabb.dtype)
+        self.update_stepSize((hi - lo).tolist())
+        self.gridSize = self.gridSize.to(dev)
+        self.struct_version = getattr(self, "struct_version", 0) + 1
+
     # ---- regulariser terms of nlf/regularizers/tensorf.py:35-96 (tensorf_base.py:1024-1057, tensorf_dynamic.py:246-286)
     def density_L1(self):
         dp, d2, _, _ = self.tables()
@@ -197,12 +332,19 @@ class _Tensorf(nn.Module):
 
     def set_iter(self, i):
         """TensorBase.set_iter (tensorf_base.py:509-553), the up-sampling half: in training mode, at the iterations of
-        `upsamp_list`, re-sample every table to the next grid of the schedule and ask for an optimiser reset.  The alpha-mask
-        update / aabb shrink of `update_AlphaMask_list` (:517-529) is not mirrored."""
+        `update_AlphaMask_list`, rebuild the occupancy mask (and shrink the aabb / crop the tables the first time); at those of
+        `upsamp_list`, re-sample every table to the next grid of the schedule and ask for an optimiser reset."""
         self.cur_iter = i
         if not self.training:
             return
         self.needs_opt_reset = False
+        if i in self.update_AlphaMask_list:  # pruning (:517-529): mask at the grid's resolution, capped at 200^3
+            reso = tuple(int(v) for v in self.gridSize.tolist())
+            if reso[0] > 200:
+                reso = (200, 200, 200)
+            new_aabb = self.updateAlphaMask(reso)
+            if i == self.update_AlphaMask_list[0]:
+                self.shrink(new_aabb)
         if i in self.upsamp_list and len(self.N_voxel_list) > 0:
             if self.use_grid_size_upsample:
                 if len(self.N_voxel_list[0]) == 0:

@@ -6,8 +6,8 @@ Only what sits on the hot path is kept: construction from the full config (``cfg
 checkpoints whose keys carry the ``render_fn.`` prefix, and -- SURVEY.md section 8 row f1 -- ``configure_optimizers`` /
 ``training_step`` (nlf/__init__.py:504-523, 634-709) over the differentiable path: image loss, manual optimisation with
 one Adam per optimiser group, the TensoRF regulariser (L1 + TV on the tables, nlf/regularizers/tensorf.py:35-96) and the grid
-up-sampling schedule with its optimiser reset (tensorf_base.py:509-553,1151-1188).  The alpha-mask / shrink step, visualisers
-and datasets are out of scope.
+up-sampling / occupancy-pruning schedule with its optimiser reset (tensorf_base.py:379-429,509-553,1151-1232).  Visualisers and
+datasets are out of scope.
 """
 from __future__ import annotations
 

@@ -140,14 +140,17 @@ def test_system_training_step_mirrors_the_reference_loop():
 
 def test_training_across_a_grid_upsampling_step_with_the_tensorf_regulariser():
     """The schedule half of the reference's loop: `set_train_iter` re-samples the tables at an `upsamp_list` iteration
-    (tensorf_base.py:509-553,1151-1188), the optimisers restart on the new Parameter objects, the TensoRF regulariser
+    (tensorf_base.py:509-553,1151-1188), rebuilds the occupancy mask and shrinks the aabb at an `update_AlphaMask_list` iteration
+    (:379-429,1190-1232), the optimisers restart on the new Parameter objects, the TensoRF regulariser
     (nlf/regularizers/tensorf.py:35-96) adds its L1 / TV terms, training continues on the fused kernels at the new grid, and the
     re-packed model renders what the oracle computes from the up-sampled parameters."""
     case = build_case("donerf_app", n=1024)
     mcfg = hb.to_cfg(hb.config.to_plain(case.model_cfg))
     mcfg.color.net.N_voxel_init, mcfg.color.net.N_voxel_final = 40 ** 3, 56 ** 3
     mcfg.color.net.upsamp_list, mcfg.color.net.lr_upsample_reset = [3], True
-    reg = {"type": "tensorf", "update_AlphaMask_list": [], "lr_decay_target_ratio": 0.1, "n_iters": 30000,
+    mcfg.color.net.update_AlphaMask_list = [5]  # occupancy mask + aabb shrink two iterations after the re-sampling
+    mcfg.color.net.alpha_mask_thre = 1e-6       # (seeded tables are far less dense than a trained scene)
+    reg = {"type": "tensorf", "update_AlphaMask_list": [5], "lr_decay_target_ratio": 0.1, "n_iters": 30000,
            "L1_weight_initial": 8e-5, "L1_weight_rest": 4e-5, "TV_weight_density": 0.05, "TV_weight_app": 0.05}
     cfg = hb.to_cfg({"model": mcfg, "training": {"ray_chunk": 1 << 20, "iters_per_epoch": 4000,
                                                  "optimizers": {"color": {"lr": 0.002}, "color_impl": {"lr": 0.001},
@@ -164,6 +167,7 @@ def test_training_across_a_grid_upsampling_step_with_the_tensorf_regulariser():
     grid1 = net.gridSize.tolist()
     assert grid1 != grid0 and all(b > a for a, b in zip(grid0, grid1)), (grid0, grid1)
     assert net.density_plane[0].shape[-1] == grid1[0] and net.density_line[0].shape[2] == grid1[2]
+    assert net.alphaMask is not None and system.regularizers[0].L1_reg_weight == 4e-5  # the pruning step ran at iteration 5
     assert losses[-1] < losses[0] and losses[-1] < losses[3], losses  # keeps improving after the re-sampling at iteration 3
     system.eval()
     with torch.no_grad():

@@ -283,3 +283,56 @@ def test_oracle_stages_match_the_reference_on_the_round_2_families():
         assert float((rgb - out["rgb"].reshape(rgb.shape)).abs().max()) <= 2e-6, name
         assert float((st["points"].reshape(n, -1) - out["_embed"]["points"].reshape(n, -1)).abs().max()) <= 2e-6, name
         assert float((st["distances"].reshape(n, -1) - out["_embed"]["distances"].reshape(n, -1)).abs().max()) <= 2e-6, name
+
+
+@pytest.mark.parametrize("name,gain", [("technicolor_z_plane", 40000.0), ("donerf_sphere", 40000.0)])
+def test_alpha_mask_update_and_shrink_match_the_reference(name, gain):
+    """The pruning step of the training schedule (tensorf_base.py:379-429,1190-1232 / tensorf_dynamic.py:443-541): dense
+    occupancy, mask, bounding box, cropped tables and corrected aabb equal the unmodified reference's on the same parameters;
+    a second mask update (which, in the static net, consults the first mask) as well."""
+    import hyperreel_b200 as hb
+    from hyperreel_b200.config import to_plain
+    from hyperreel_b200.state import _Color, seeded_state_dict
+
+    ds = {"num_keyframes": 4, "num_frames": 6, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y"}
+    cfg = hb.load_model_yaml(f"{ref_shim.REFERENCE_ROOT}/conf/experiment/model/{name}.yaml")
+    cfg.color.net.N_voxel_init = cfg.color.net.N_voxel_final = 13 ** 3
+    sig = hb.lower(cfg, ds)
+    sd = seeded_state_dict(sig, seed=8)
+    # occupancy confined to a corner region, so that the box of occupied voxels is a strict subset of the grid
+    # (empty for x in the lower half of the box: groups 0 and 1 have x as their planes' column axis, group 2 as its line's axis)
+    for k in list(sd):
+        if "density_plane" in k and "time" not in k and sd[k].numel() > 0:
+            t = sd[k].clone() * gain
+            if not k.endswith(".2"):
+                t[..., : t.shape[-1] // 2] = 0
+            sd[k] = t
+        if "density_line.2" in k and sd[k].numel() > 0:
+            t = sd[k].clone()
+            t[..., : t.shape[-2] // 2, :] = 0
+            sd[k] = t
+    ref = ref_shim.build_reference(to_plain(cfg), ds)
+    ref.load_state_dict(sd, strict=False)
+    rnet = ref.model.color_model.net
+    mine = _Color(sig, hb.state.default_grid(sig))
+    mine.load_state_dict({k[len("model.color_model."):]: v for k, v in sd.items() if k.startswith("model.color_model.")}, strict=False)
+    reso = tuple(rnet.gridSize.tolist())
+    with torch.no_grad():
+        a_ref, _ = rnet.getDenseAlpha(reso)
+        a_mine, _ = mine.net.getDenseAlpha(reso)
+    # (the reference evaluates slab by slab, here in one batch: the same values up to the last bit or two)
+    assert float((a_ref - a_mine).abs().max()) <= 1e-6 and float(a_ref.max()) > 0.05 > 0.001 > float(a_ref.min())
+    box_ref = rnet.updateAlphaMask(reso)
+    box_mine = mine.net.updateAlphaMask(reso)
+    assert torch.equal(box_ref, box_mine)
+    assert torch.equal(rnet.alphaMask.alpha_volume, mine.net.alphaMask.volume)
+    rnet.shrink(box_ref)
+    mine.net.shrink(box_mine)
+    assert rnet.gridSize.tolist() == mine.net.gridSize.tolist() and any(g < r for g, r in zip(rnet.gridSize.tolist(), reso))
+    assert torch.equal(rnet.aabb, mine.net.aabb)
+    got = mine.state_dict()
+    for k, v in rnet.state_dict().items():
+        if any(t in k for t in ("plane", "line")):
+            assert torch.equal(v, got["net." + k]), k
+    reso2 = tuple(rnet.gridSize.tolist())
+    assert torch.equal(rnet.updateAlphaMask(reso2), mine.net.updateAlphaMask(reso2))
