@@ -336,3 +336,69 @@ def test_alpha_mask_update_and_shrink_match_the_reference(name, gain):
             assert torch.equal(v, got["net." + k]), k
     reso2 = tuple(rnet.gridSize.tolist())
     assert torch.equal(rnet.updateAlphaMask(reso2), mine.net.updateAlphaMask(reso2))
+
+
+def test_lowered_constants_equal_the_reference_constructors_on_every_shipped_yaml():
+    """hyperreel_b200.signature.lower (product host code) against the objects the unmodified reference builds from the same YAML
+    and dataset facts: base primitives (`samples`), their spacing (`z_scale`), the mask bounds, the contraction radii, and the
+    colour net's scalars -- for all 45 shipped model YAMLs that run, under two sets of dataset facts."""
+    import glob
+    import os
+
+    import hyperreel_b200 as hb
+    from hyperreel_b200 import lib as L
+    from hyperreel_b200.config import to_plain
+    from hyperreel_b200.signature import UnsupportedPipeline
+
+    ref_shim.install()
+    facts = [
+        {"num_keyframes": 12, "num_frames": 50, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y",
+         "bbox_min": [-1.5, -1.25, -1.0], "bbox_max": [1.5, 1.25, 1.0], "total_images_per_frame": 5, "val_all": True},
+        {"num_keyframes": 7, "num_frames": 30, "near": 0.25, "far": 6.0, "depth_range": [0.75, 4.0], "name": "x", "collection": "y",
+         "bbox_min": [-0.5, -2.0, -1.5], "bbox_max": [2.5, 1.0, 0.5], "total_images_per_frame": 3, "val_all": False},
+    ]
+    checked = 0
+    for f in sorted(glob.glob(os.path.join(ref_shim.REFERENCE_ROOT, "conf/experiment/model/*.yaml"))):
+        cfg = hb.load_model_yaml(f)
+        if cfg is None:
+            continue
+        cfg.color.net.N_voxel_init = cfg.color.net.N_voxel_final = 12 ** 3
+        for ds in facts:
+            try:
+                sig = hb.lower(cfg, ds)
+            except UnsupportedPipeline:
+                continue
+            c = sig.cfg
+            ref = ref_shim.build_reference(to_plain(cfg), ds)
+            embs = ref.model.embedding_model.embeddings
+            keys = list(to_plain(cfg)["embedding"]["embeddings"].keys())
+            isects = [embs[i].intersect_fn for i, k in enumerate(keys) if cfg.embedding.embeddings[k].type == "ray_intersect"]
+            it = isects[-1]
+            S = c.n_samples
+            name = os.path.basename(f)
+            assert torch.equal(torch.tensor(list(c.samples)[:S]), it.samples.reshape(-1).float()), name
+            zs = torch.as_tensor(it.z_scale).reshape(-1).float()
+            if c.isect_type == L.ISECT_VOXEL:
+                assert torch.equal(torch.tensor(list(c.z_scale3)), zs), name
+            else:
+                assert abs(c.z_scale - float(zs[0])) <= 1e-7 * max(1.0, abs(float(zs[0]))), name
+            f32 = lambda v: float(torch.tensor(float(v), dtype=torch.float32))  # the struct holds fp32, like the tensors they meet
+            if it.cur_iter <= it.mask_stop_iters:  # otherwise nothing is masked and the bounds are irrelevant
+                assert c.isect_near == f32(it.near) and c.isect_far == f32(it.far), name
+            if c.contract_type == L.CONTRACT_MIPNERF:
+                cf = it.contract_fn
+                assert (c.contract_start_radius, c.contract_end_radius) == (f32(cf.contract_start_radius), f32(cf.contract_end_radius)), name
+                assert (c.contract_start_distance, c.contract_end_distance) == (f32(cf.contract_start_distance), f32(cf.contract_end_distance)), name
+            if c.cascade:
+                it0 = isects[0]
+                assert torch.equal(torch.tensor(list(c.pre_samples_tab)[:c.pre_samples]), it0.samples.reshape(-1).float()), name
+                assert abs(c.pre_z_scale - float(torch.as_tensor(it0.z_scale).reshape(-1)[0])) <= 1e-7, name
+            net = ref.model.color_model.net
+            assert c.distance_scale == f32(net.distance_scale) and c.weight_thre == f32(net.rayMarch_weight_thres), name
+            assert bool(c.white_bg) == bool(net.white_bg) and bool(c.black_bg) == bool(net.black_bg), name
+            assert [c.aabb[i] for i in range(6)] == [f32(v) for v in net.aabb.reshape(-1)], name
+            assert hb.state.default_grid(sig) == net.gridSize.tolist(), name
+            if c.dynamic:
+                assert (c.num_keyframes, c.num_frames) == (int(net.num_keyframes), int(net.total_num_frames)), name
+            checked += 1
+    assert checked == 90
