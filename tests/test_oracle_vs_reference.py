@@ -402,3 +402,61 @@ def test_lowered_constants_equal_the_reference_constructors_on_every_shipped_yam
                 assert (c.num_keyframes, c.num_frames) == (int(net.num_keyframes), int(net.total_num_frames)), name
             checked += 1
     assert checked == 90
+
+
+def test_lowered_activations_equal_the_reference_modules_on_every_shipped_yaml():
+    """signature.resolve_activation lowers every head / intersect / flow / offset activation to y = f(x * inner + shift) * outer
+    (the form the kernels evaluate): the same numbers as the reference's activation modules at render iteration, for every
+    activation of all shipped YAMLs that lower."""
+    import glob
+    import os
+
+    import hyperreel_b200 as hb
+    from hyperreel_b200 import lib as L
+    from hyperreel_b200.config import epochs_to_iters, to_plain
+    from hyperreel_b200.signature import RENDER_ITER, UnsupportedPipeline, resolve_activation
+
+    ref_shim.install()
+    from nlf.activations import get_activation
+
+    def walk(o, path=""):
+        if isinstance(o, dict):
+            for k, v in o.items():
+                if k.endswith("activation") and (isinstance(v, (dict, str))):
+                    yield path + "/" + k, v
+                if isinstance(v, (dict, list)):
+                    yield from walk(v, path + "/" + k)
+        elif isinstance(o, list):
+            for i, v in enumerate(o):
+                yield from walk(v, f"{path}[{i}]")
+
+    ds = {"num_keyframes": 12, "num_frames": 50, "near": 0.5, "far": 10.0, "depth_range": [0.5, 10.0], "name": "x", "collection": "y",
+          "bbox_min": [-1.5, -1.25, -1.0], "bbox_max": [1.5, 1.25, 1.0], "total_images_per_frame": 5, "val_all": True}
+    x = torch.linspace(-6.0, 6.0, 97)
+    n = 0
+    for f in sorted(glob.glob(os.path.join(ref_shim.REFERENCE_ROOT, "conf/experiment/model/*.yaml"))):
+        cfg = hb.load_model_yaml(f)
+        if cfg is None:
+            continue
+        try:
+            hb.lower(cfg, ds)
+        except UnsupportedPipeline:
+            continue
+        plain = epochs_to_iters(to_plain(cfg), 1)
+        for path, acfg in walk(plain["embedding"]):
+            if isinstance(acfg, dict) and "type" not in acfg:
+                continue
+            try:
+                act = resolve_activation(hb.to_cfg(acfg) if isinstance(acfg, dict) else acfg, RENDER_ITER)
+            except UnsupportedPipeline:
+                continue  # an activation of an embedding the fused path does not evaluate (e.g. angular flow): never lowered
+            mod = get_activation(ref_shim.to_attr(acfg) if isinstance(acfg, dict) else acfg)
+            if hasattr(mod, "set_iter"):
+                mod.set_iter(RENDER_ITER)
+            want = mod(x.clone())
+            v = x * act.inner_fac + act.shift
+            v = torch.sigmoid(v) if act.kind == L.ACT_SIGMOID else (torch.tanh(v) if act.kind == L.ACT_TANH else v)
+            got = v * act.outer_fac
+            assert float((got - want).abs().max()) <= 1e-6, (os.path.basename(f), path)
+            n += 1
+    assert n > 300
